@@ -1,0 +1,163 @@
+"""`Bus`: a thin numpy-friendly wrapper over the libcpbus C-ABI (include/cpbus.h).
+
+One `Bus` = one GPU's shard of subscriber mailboxes.  Every method maps 1:1 to a
+`cpbus_*` entry point; no event ever takes a Python/CPU data path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+EVENT_DTYPE = np.dtype([("seq", "<u8"), ("ts_ns", "<u8"), ("code", "<u4"), ("source_id", "<u4"),
+                        ("target", "<u4"), ("flags", "<u4")])
+assert EVENT_DTYPE.itemsize == 32
+
+
+class Bus:
+    def __init__(self, n_max_subs: int, ring_cap: int = 1024, batch_cap: int = 256, timers_per_sub: int = 0,
+                 lossless: bool = False, digest: bool = True, device: int = -1, sub_id_base: int = 0,
+                 store_path: int = nat.STORE_AUTO, stream: int | None = None, grid_ctas: int = 0):
+        self._lib = nat.load()
+        cfg = nat.Config()
+        cfg.n_max_subs, cfg.ring_cap, cfg.batch_cap, cfg.timers_per_sub = n_max_subs, ring_cap, batch_cap, timers_per_sub
+        cfg.flags = (nat.CFG_LOSSLESS if lossless else 0) | (nat.CFG_DIGEST if digest else 0)
+        cfg.device, cfg.sub_id_base, cfg.store_path, cfg.grid_ctas = device, sub_id_base, store_path, grid_ctas
+        cfg.stream = C.c_void_p(stream) if stream else None
+        self._h = C.c_void_p()
+        nat.check(self._lib.cpbus_create(C.byref(cfg), C.byref(self._h)), "cpbus_create")
+        self.ring_cap, self.batch_cap, self.sub_id_base = ring_cap, batch_cap, sub_id_base
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if self._h:
+            self._lib.cpbus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- intern ------------------------------------------------------------
+    def intern(self, s: str) -> int:
+        raw = s.encode()
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_intern(self._h, raw, len(raw), C.byref(out)), "cpbus_intern")
+        return out.value
+
+    def source(self, source_id: int) -> str:
+        n = C.c_size_t()
+        nat.check(self._lib.cpbus_source(self._h, source_id, None, 0, C.byref(n)), "cpbus_source")
+        buf = C.create_string_buffer(max(1, n.value))
+        nat.check(self._lib.cpbus_source(self._h, source_id, buf, n.value, C.byref(n)), "cpbus_source")
+        return buf.raw[: n.value].decode()
+
+    # -- membership --------------------------------------------------------
+    def subscribe(self, mask: int = nat.MASK_ALL) -> int:
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_subscribe(self._h, mask, C.byref(out)), "cpbus_subscribe")
+        return out.value
+
+    def subscribe_many(self, masks) -> int:
+        m = np.ascontiguousarray(masks, dtype=np.uint32)
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_subscribe_many(self._h, m.ctypes.data, m.size, C.byref(out)), "cpbus_subscribe_many")
+        return out.value
+
+    def unsubscribe(self, sub_id: int):
+        nat.check(self._lib.cpbus_unsubscribe(self._h, sub_id), "cpbus_unsubscribe")
+
+    # -- timers ------------------------------------------------------------
+    def timer_add(self, sub_id: int, period_ns: int, source_id: int, oneshot: bool = False) -> int:
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_timer_add(self._h, sub_id, period_ns, source_id, int(oneshot), C.byref(out)), "cpbus_timer_add")
+        return out.value
+
+    def timer_add_many(self, first_sub: int, n: int, period_ns: int, source_ids=None, source_id0: int = 0, oneshot: bool = False):
+        ptr = None
+        if source_ids is not None:
+            arr = np.ascontiguousarray(source_ids, dtype=np.uint32)
+            ptr = arr.ctypes.data
+        nat.check(self._lib.cpbus_timer_add_many(self._h, first_sub, n, period_ns, ptr, source_id0, int(oneshot)), "cpbus_timer_add_many")
+
+    def timer_cancel(self, timer_id: int):
+        nat.check(self._lib.cpbus_timer_cancel(self._h, timer_id), "cpbus_timer_cancel")
+
+    # -- hot path ----------------------------------------------------------
+    def publish(self, code: int, source_id: int = 0) -> int:
+        ev = nat.Event(0, 0, code, source_id, 0, 0)
+        return self._lib.cpbus_publish(self._h, C.byref(ev), 1)
+
+    def publish_many(self, events: np.ndarray) -> int:
+        """events: EVENT_DTYPE array (only code/source_id are read)."""
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        return self._lib.cpbus_publish(self._h, ev.ctypes.data, ev.size)
+
+    def send(self, sub_id: int, code: int, source_id: int = 0) -> int:
+        ev = nat.Event(0, 0, code, source_id, 0, 0)
+        return self._lib.cpbus_send(self._h, sub_id, C.byref(ev))
+
+    def advance(self, now_ns: int) -> int:
+        return self._lib.cpbus_advance(self._h, now_ns)
+
+    def flush(self) -> int:
+        return self._lib.cpbus_flush(self._h)
+
+    def sync(self):
+        nat.check(self._lib.cpbus_sync(self._h), "cpbus_sync")
+
+    def publish_device(self, dev_ptr: int, n: int, watermark_ns: int) -> int:
+        return self._lib.cpbus_publish_device(self._h, C.c_void_p(dev_ptr), n, watermark_ns)
+
+    # -- consumer side -----------------------------------------------------
+    def drain(self, sub_id: int, cap: int | None = None):
+        cap = cap or self.ring_cap
+        out = np.zeros(cap, dtype=EVENT_DTYPE)
+        n, lost = C.c_size_t(), C.c_uint64()
+        nat.check(self._lib.cpbus_drain(self._h, sub_id, out.ctypes.data, cap, C.byref(n), C.byref(lost)), "cpbus_drain")
+        return out[: n.value]
+
+    def peek_window(self, sub_id: int, cap: int | None = None) -> np.ndarray:
+        cap = cap or self.ring_cap
+        out = np.zeros(cap, dtype=EVENT_DTYPE)
+        n = C.c_size_t()
+        nat.check(self._lib.cpbus_peek_window(self._h, sub_id, out.ctypes.data, cap, C.byref(n)), "cpbus_peek_window")
+        return out[: n.value]
+
+    def digests(self, first_sub: int, n: int):
+        out = np.zeros(n, dtype=[("count", "<u8"), ("digest", "<u8")])
+        nat.check(self._lib.cpbus_digest(self._h, first_sub, n, out.ctypes.data), "cpbus_digest")
+        return out
+
+    def digest_fold(self, first_sub: int, n: int):
+        out = (C.c_uint64 * 4)()
+        nat.check(self._lib.cpbus_digest_fold(self._h, first_sub, n, C.byref(out)), "cpbus_digest_fold")
+        return tuple(out)
+
+    def debug_events(self):
+        out = np.zeros(10, dtype=EVENT_DTYPE)
+        n = C.c_size_t()
+        nat.check(self._lib.cpbus_debug_events(self._h, out.ctypes.data, 10, C.byref(n)), "cpbus_debug_events")
+        return out[: n.value]
+
+    def stats(self) -> dict:
+        st = nat.Stats()
+        nat.check(self._lib.cpbus_stats(self._h, C.byref(st)), "cpbus_stats")
+        d = {k: getattr(st, k) for k, _ in nat.Stats._fields_ if k != "published_by_code"}
+        d["published_by_code"] = list(st.published_by_code)
+        return d
+
+    def device_ptrs(self) -> dict:
+        ring, tail, mask, dig = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nat.check(self._lib.cpbus_device_ptrs(self._h, C.byref(ring), C.byref(tail), C.byref(mask), C.byref(dig)), "cpbus_device_ptrs")
+        return {"ring": ring.value, "tail": tail.value, "mask": mask.value, "digest": dig.value}

@@ -1,0 +1,693 @@
+// cpbus.cu — libcpbus: C-ABI (include/cpbus.h) over the sm_100a kernels.
+//
+// Host-side bookkeeping that the reference keeps in Go (events/bus.go): the
+// registry, the 10-slot debug ring, per-code publish counts, the Source intern
+// table, the virtual clock, staging of published events into pinned batches.
+// There is NO CPU data path: without a CUDA device cpbus_create fails with
+// CPBUS_ENODEV, and nothing here touches oracle/.
+#include "cpbus_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace cpbus_dev;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "%s:%d %s: %s", __FILE__, __LINE__, #call,          \
+               cudaGetErrorString(e_));                                                            \
+      return CPBUS_ECUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+struct HostTimer { bool active = false, oneshot = false; uint64_t period = 0, next_due = 0; uint32_t source_id = 0; };
+
+}  // namespace
+
+struct cpbus {
+  cpbus_config cfg{};
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint32_t N = 0, R = 0, B = 0, K = 0;
+  int store = CPBUS_STORE_V8;
+  bool lossless = false, use_digest = false;
+
+  // HBM-resident state (SoA, one entry per subscriber of this shard)
+  cpbus_event* d_ring = nullptr;          // N * R records: each mailbox is one contiguous 32*R-byte ring
+  unsigned long long *d_tail = nullptr, *d_head = nullptr, *d_digest = nullptr;
+  uint32_t* d_mask = nullptr;
+  DevTimer* d_timers = nullptr;           // N * K
+  DevStats* d_stats = nullptr;
+  unsigned long long* d_fold = nullptr;   // 4 words
+  cpbus_event* d_batch[2] = {nullptr, nullptr};
+  cpbus_event* h_batch[2] = {nullptr, nullptr};   // pinned staging
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  DevStats* h_stats = nullptr;            // pinned
+  unsigned long long* h_fold = nullptr;   // pinned
+  int cur = 0;
+  size_t n_staged = 0;
+
+  // registry mirror (events/bus.go:13 `registry map[*Subscriber]bool`)
+  std::vector<uint32_t> h_mask;
+  std::vector<uint8_t> h_active;
+  std::vector<size_t> oneshot_idx;        // armed one-shot timers (index into h_timers)
+  std::vector<HostTimer> h_timers;        // N*K, allocated on first timer
+  uint32_t n_next = 0, n_active = 0, n_timers = 0;
+  uint64_t min_period = UINT64_MAX;       // conservative lower bound over armed periodic timers
+
+  // clock and ordinals
+  uint64_t now = 0, last_watermark = 0, seq = 0;
+
+  // DebugEvents ring (events/bus.go:18-21, 24-54)
+  int dbg_head = -1, dbg_tail = 0;
+  cpbus_event dbg[10]{};
+
+  // intern table (Event.Source string <-> u32)
+  std::unordered_map<std::string, uint32_t> intern;
+  std::vector<std::string> sources;
+
+  cpbus_stats_t st{};
+  std::mutex mu;   // drain/stats from a second thread
+};
+
+namespace {
+
+int dev_guard(cpbus* b) {
+  CK(cudaSetDevice(b->device));
+  return CPBUS_OK;
+}
+
+uint32_t mask_word(const cpbus* b, uint32_t local) {
+  uint32_t hint = 0;
+  if (b->K && !b->h_timers.empty())
+    for (uint32_t k = 0; k < b->K; k++)
+      if (b->h_timers[(size_t)local * b->K + k].active) hint = k + 1;
+  if (!b->h_active[local]) return 0;
+  return (b->h_mask[local] & CPBUS_MASK_ALL) | (hint << kTimerHintShift) | kActiveBit;
+}
+
+void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
+  b->dbg[(b->dbg_head + 1) % 10] = e;
+  int old = b->dbg_head;
+  b->dbg_head = (b->dbg_head + 1) % 10;
+  if (old != -1 && b->dbg_head == b->dbg_tail) b->dbg_tail = (b->dbg_tail + 1) % 10;
+}
+
+template <int STORE>
+int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(fanout_kernel<STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  fanout_kernel<STORE><<<grid, kThreads, smem, b->stream>>>(p);
+  CK(cudaGetLastError());
+  return CPBUS_OK;
+}
+
+// fan out `n` records at d_src with watermark w (all checks done by the caller)
+int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
+  if (b->n_next == 0) return CPBUS_OK;
+  if (n == 0 && b->n_timers == 0) return CPBUS_OK;
+  FanoutParams p{};
+  p.batch = d_src; p.ring = b->d_ring; p.tail = b->d_tail; p.head = b->d_head; p.digest = b->d_digest;
+  p.mask = b->d_mask; p.timers = b->d_timers; p.stats = b->d_stats; p.w_now = w; p.n_ev = n;
+  p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
+  p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
+  p.smem_cap = (n + 31u) & ~31u;
+  const size_t smem = fanout_smem_bytes(p.smem_cap);
+  const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
+  uint32_t grid = b->cfg.grid_ctas;
+  if (!grid) {
+    // persistent-style grid: a multiple of the SM count, as many CTAs per SM as shared memory allows (<= 4)
+    uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 1024)));
+    grid = (uint32_t)b->sm_count * per_sm;
+  }
+  grid = std::max(1u, std::min(grid, need));
+  int rc;
+  switch (b->store) {
+    case CPBUS_STORE_V4: rc = launch_fanout_t<CPBUS_STORE_V4>(b, p, grid, smem); break;
+    case CPBUS_STORE_BULK: rc = launch_fanout_t<CPBUS_STORE_BULK>(b, p, grid, smem); break;
+    default: rc = launch_fanout_t<CPBUS_STORE_V8>(b, p, grid, smem); break;
+  }
+  if (rc) return rc;
+  b->st.batches++; b->st.kernel_launches++;
+  b->last_watermark = w;
+  return CPBUS_OK;
+}
+
+// lossless admission (reference: the sender blocks on a full channel)
+int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) {
+  *ok = true;
+  if (!b->lossless || b->n_next == 0) return CPBUS_OK;
+  CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, sizeof(unsigned long long), b->stream));
+  const uint32_t threads = 256, grid = (b->n_next + threads - 1) / threads;
+  admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_mask, b->d_tail, b->d_head, b->d_timers, b->n_next,
+                                                b->R, b->K, b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats);
+  CK(cudaGetLastError());
+  b->st.kernel_launches++;
+  CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  *ok = b->h_stats->admit_overflow == 0;
+  return CPBUS_OK;
+}
+
+// host mirror of one-shot timers that have fired on the device (events/timer.go:19-33):
+// a one-shot whose due time is <= the last launched watermark has disarmed itself.
+void retire_oneshots(cpbus* b, uint64_t w) {
+  size_t keep = 0;
+  for (size_t i = 0; i < b->oneshot_idx.size(); i++) {
+    HostTimer& t = b->h_timers[b->oneshot_idx[i]];
+    if (t.active && t.oneshot && t.next_due <= w) { t.active = false; b->n_timers--; continue; }
+    if (t.active && t.oneshot) b->oneshot_idx[keep++] = b->oneshot_idx[i];
+  }
+  b->oneshot_idx.resize(keep);
+  if (b->n_timers == 0) b->min_period = UINT64_MAX;
+}
+
+int flush_staged(cpbus* b, uint64_t w) {
+  const uint32_t n = (uint32_t)b->n_staged;
+  if (n == 0 && (b->n_timers == 0 || w == b->last_watermark)) return CPBUS_OK;
+  const int c = b->cur;
+  if (n) CK(cudaMemcpyAsync(b->d_batch[c], b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaEventRecord(b->h2d_done[c], b->stream));
+  bool ok = true;
+  int rc = admit(b, b->d_batch[c], n, w, &ok);
+  if (rc) return rc;
+  if (!ok) return CPBUS_EAGAIN;   // staged events stay staged; drain and call flush again
+  rc = launch_fanout(b, b->d_batch[c], n, w);
+  if (rc) return rc;
+  b->n_staged = 0;
+  b->cur ^= 1;
+  CK(cudaEventSynchronize(b->h2d_done[b->cur]));   // the buffer we are about to overwrite has left the host
+  return CPBUS_OK;
+}
+
+uint64_t max_window(const cpbus* b) {
+  if (!b->K || b->n_timers == 0 || b->min_period == UINT64_MAX) return UINT64_MAX;
+  const uint64_t J = 32u / b->K;
+  return b->min_period > UINT64_MAX / J ? UINT64_MAX : b->min_period * J;
+}
+
+int stage_one(cpbus* b, uint32_t code, uint32_t source_id, uint32_t target, uint32_t flags) {
+  if (b->n_staged == b->B) { int rc = flush_staged(b, b->now); if (rc) return rc; }
+  cpbus_event& e = b->h_batch[b->cur][b->n_staged++];
+  e.seq = b->seq++; e.ts_ns = b->now; e.code = code; e.source_id = source_id; e.target = target; e.flags = flags;
+  return CPBUS_OK;
+}
+
+bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+}  // namespace
+
+extern "C" {
+
+uint32_t cpbus_abi_version(void) { return 1; }
+
+const char* cpbus_last_cuda_error(void) { return g_cuda_err; }
+
+const char* cpbus_strerror(int s) {
+  switch (s) {
+    case CPBUS_OK: return "ok";
+    case CPBUS_EINVAL: return "invalid argument";
+    case CPBUS_ENOMEM: return "out of memory";
+    case CPBUS_ECUDA: return "CUDA error";
+    case CPBUS_EAGAIN: return "mailbox full (lossless mode): drain and retry";
+    case CPBUS_ENOSPC: return "capacity exhausted";
+    case CPBUS_ENOENT: return "no such subscriber or timer";
+    case CPBUS_ECLOSED: return "subscriber already unsubscribed";
+    case CPBUS_ENODEV: return "no CUDA device (libcpbus has no CPU fallback)";
+    case CPBUS_EORDER: return "clock moved backwards, batch unsorted or timer window exceeded";
+    default: return "unknown status";
+  }
+}
+
+// EventCode.String — events/eventcode_string.go:5-15
+const char* cpbus_code_name(int code) {
+  static const char* const names[CPBUS_N_CODES] = {
+      "None", "ExitSuccess", "ExitFailed", "Stopping", "Stopped", "StatusHealthy", "StatusUnhealthy", "StatusChanged",
+      "TimerExpired", "EnterMaintenance", "ExitMaintenance", "Error", "Quit", "Metric", "Startup", "Shutdown", "Signal"};
+  return (code < 0 || code >= CPBUS_N_CODES) ? nullptr : names[code];
+}
+
+// FromString — events/events.go:52-86
+int cpbus_code_from_string(const char* name) {
+  if (!name) return -1;
+  static const std::unordered_map<std::string, int> table = {
+      {"exitSuccess", CPBUS_EXIT_SUCCESS}, {"exitFailed", CPBUS_EXIT_FAILED}, {"stopping", CPBUS_STOPPING},
+      {"stopped", CPBUS_STOPPED}, {"healthy", CPBUS_STATUS_HEALTHY}, {"unhealthy", CPBUS_STATUS_UNHEALTHY},
+      {"changed", CPBUS_STATUS_CHANGED}, {"timerExpired", CPBUS_TIMER_EXPIRED},
+      {"enterMaintenance", CPBUS_ENTER_MAINTENANCE}, {"exitMaintenance", CPBUS_EXIT_MAINTENANCE},
+      {"error", CPBUS_ERROR}, {"quit", CPBUS_QUIT}, {"startup", CPBUS_STARTUP}, {"shutdown", CPBUS_SHUTDOWN},
+      {"SIGHUP", CPBUS_SIGNAL}, {"SIGUSR2", CPBUS_SIGNAL}};
+  auto it = table.find(name);
+  return it == table.end() ? -1 : it->second;
+}
+
+uint64_t cpbus_record_hash(const cpbus_event* e) {
+  return record_hash_words(e->seq, e->ts_ns, (uint64_t)e->code | ((uint64_t)e->source_id << 32),
+                           (uint64_t)e->target | ((uint64_t)e->flags << 32));
+}
+uint64_t cpbus_digest_multiplier(void) { return kDigestP; }
+
+int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
+  if (!cfg || !out) return CPBUS_EINVAL;
+  *out = nullptr;
+  const uint32_t R = cfg->ring_cap ? cfg->ring_cap : 1024;
+  const uint32_t B = cfg->batch_cap ? cfg->batch_cap : std::min(256u, R / 2);
+  const uint32_t K = cfg->timers_per_sub;
+  if (!cfg->n_max_subs || !is_pow2(R) || R < 64 || B == 0 || B > R / 2 || (B % 32) != 0 || B > 2048) return CPBUS_EINVAL;
+  if (!(K == 0 || K == 1 || K == 2 || K == 4 || K == 8)) return CPBUS_EINVAL;
+  if (cfg->store_path > CPBUS_STORE_BULK) return CPBUS_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device visible");
+    return CPBUS_ENODEV;
+  }
+  cpbus* b = new (std::nothrow) cpbus();
+  if (!b) return CPBUS_ENOMEM;
+  b->cfg = *cfg; b->cfg.ring_cap = R; b->cfg.batch_cap = B;
+  b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
+  b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
+  b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  int rc = CPBUS_OK;
+  auto fail = [&](int code) { cpbus_destroy(b); return code; };
+  if (cfg->device >= 0) b->device = cfg->device;
+  else if (cudaGetDevice(&b->device) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (b->device >= ndev) return fail(CPBUS_EINVAL);
+  if ((rc = dev_guard(b))) return fail(rc);
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, b->device) == cudaSuccess) b->sm_count = prop.multiProcessorCount;
+  if (cfg->stream) b->stream = (cudaStream_t)cfg->stream;
+  else {
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
+    b->own_stream = true;
+  }
+  const size_t N = b->N;
+#define ALLOC(ptr, bytes)                                                                     \
+  if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) {                                   \
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(%zu) failed", (size_t)(bytes));     \
+    return fail(CPBUS_ENOMEM);                                                                \
+  }
+  ALLOC(b->d_ring, N * R * sizeof(cpbus_event));
+  ALLOC(b->d_tail, N * 8); ALLOC(b->d_head, N * 8); ALLOC(b->d_digest, N * 8); ALLOC(b->d_mask, N * 4);
+  if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
+  ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32);
+  for (int i = 0; i < 2; i++) {
+    ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));
+    if (cudaMallocHost((void**)&b->h_batch[i], (size_t)B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
+    if (cudaEventCreateWithFlags(&b->h2d_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
+  }
+#undef ALLOC
+  if (cudaMallocHost((void**)&b->h_stats, sizeof(DevStats)) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  if (cudaMallocHost((void**)&b->h_fold, 32) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  // rings are NOT cleared: a slot is only ever read after it has been written (head/tail bound every read)
+  bool ok = cudaMemsetAsync(b->d_tail, 0, N * 8, b->stream) == cudaSuccess &&
+            cudaMemsetAsync(b->d_head, 0, N * 8, b->stream) == cudaSuccess &&
+            cudaMemsetAsync(b->d_digest, 0, N * 8, b->stream) == cudaSuccess &&
+            cudaMemsetAsync(b->d_mask, 0, N * 4, b->stream) == cudaSuccess &&
+            cudaMemsetAsync(b->d_stats, 0, sizeof(DevStats), b->stream) == cudaSuccess &&
+            (!K || cudaMemsetAsync(b->d_timers, 0, N * K * sizeof(DevTimer), b->stream) == cudaSuccess) &&
+            cudaStreamSynchronize(b->stream) == cudaSuccess;
+  if (!ok) return fail(CPBUS_ECUDA);
+  b->h_mask.assign(N, 0);
+  b->h_active.assign(N, 0);
+  b->intern.emplace(std::string(), 0u);   // "" -> 0 so that NonEvent == {None, 0} (events/events.go:45)
+  b->sources.emplace_back();
+  *out = b;
+  return CPBUS_OK;
+}
+
+int cpbus_destroy(cpbus_t* b) {
+  if (!b) return CPBUS_EINVAL;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_ring); cudaFree(b->d_tail); cudaFree(b->d_head); cudaFree(b->d_digest); cudaFree(b->d_mask);
+  cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(b->d_batch[i]);
+    if (b->h_batch[i]) cudaFreeHost(b->h_batch[i]);
+    if (b->h2d_done[i]) cudaEventDestroy(b->h2d_done[i]);
+  }
+  if (b->h_stats) cudaFreeHost(b->h_stats);
+  if (b->h_fold) cudaFreeHost(b->h_fold);
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return CPBUS_OK;
+}
+
+int cpbus_intern(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
+  if (!b || (!s && len) || !source_id) return CPBUS_EINVAL;
+  std::string key(s ? s : "", len);
+  auto it = b->intern.find(key);
+  if (it != b->intern.end()) { *source_id = it->second; return CPBUS_OK; }
+  if (b->sources.size() >= 0xFFFFFFF0u) return CPBUS_ENOSPC;
+  const uint32_t id = (uint32_t)b->sources.size();
+  b->sources.push_back(key);
+  b->intern.emplace(std::move(key), id);
+  *source_id = id;
+  return CPBUS_OK;
+}
+
+int cpbus_source(cpbus_t* b, uint32_t id, char* out, size_t cap, size_t* len) {
+  if (!b || id >= b->sources.size()) return b ? CPBUS_ENOENT : CPBUS_EINVAL;
+  const std::string& s = b->sources[id];
+  if (len) *len = s.size();
+  if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
+  return CPBUS_OK;
+}
+
+int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t* first_sub_id) {
+  if (!b || !n) return CPBUS_EINVAL;
+  if ((uint64_t)b->n_next + n > b->N) return CPBUS_ENOSPC;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;   // ordered with publishes (events/bus.go:105-107 takes the same lock)
+  const uint32_t first = b->n_next;
+  std::vector<uint32_t> words(n);
+  for (uint32_t i = 0; i < n; i++) {
+    b->h_mask[first + i] = (masks ? masks[i] : CPBUS_MASK_ALL) & CPBUS_MASK_ALL;
+    words[i] = b->h_mask[first + i] | kActiveBit;
+    b->h_active[first + i] = 1;
+  }
+  CK(cudaMemcpyAsync(b->d_mask + first, words.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->n_next += n; b->n_active += n;
+  if (first_sub_id) *first_sub_id = b->cfg.sub_id_base + first;
+  return CPBUS_OK;
+}
+
+int cpbus_subscribe(cpbus_t* b, uint32_t mask, uint32_t* sub_id) { return cpbus_subscribe_many(b, &mask, 1, sub_id); }
+
+int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
+  if (!b) return CPBUS_EINVAL;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  // second Unsubscribe drives the WaitGroup negative in Go (events/bus.go:121) => panic
+  if (!b->h_active[l]) return CPBUS_ECLOSED;
+  b->h_active[l] = 0;
+  const uint32_t word = 0;
+  CK(cudaMemcpyAsync(b->d_mask + l, &word, 4, cudaMemcpyHostToDevice, b->stream));
+  if (b->K && !b->h_timers.empty()) {
+    for (uint32_t k = 0; k < b->K; k++) {
+      HostTimer& t = b->h_timers[(size_t)l * b->K + k];
+      if (t.active) { t.active = false; b->n_timers--; }
+    }
+    CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K, 0, b->K * sizeof(DevTimer), b->stream));
+  }
+  CK(cudaStreamSynchronize(b->stream));
+  b->n_active--;
+  return CPBUS_OK;
+}
+
+static int push_mask_words(cpbus* b, uint32_t first, uint32_t n) {
+  std::vector<uint32_t> words(n);
+  for (uint32_t i = 0; i < n; i++) words[i] = mask_word(b, first + i);
+  CK(cudaMemcpyAsync(b->d_mask + first, words.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return CPBUS_OK;
+}
+
+int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id) {
+  if (!b || !period_ns) return CPBUS_EINVAL;
+  if (!b->K) return CPBUS_ENOSPC;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  if (b->h_timers.empty()) b->h_timers.resize((size_t)b->N * b->K);
+  retire_oneshots(b, b->last_watermark);
+  if (!b->h_active[l]) return CPBUS_ECLOSED;
+  for (uint32_t k = 0; k < b->K; k++) {
+    HostTimer& t = b->h_timers[(size_t)l * b->K + k];
+    if (t.active) continue;
+    t.active = true; t.oneshot = oneshot != 0; t.period = period_ns; t.next_due = b->now + period_ns; t.source_id = source_id;
+    DevTimer d{}; d.next_due = t.next_due; d.period = period_ns; d.source_id = source_id; d.fired = 0;
+    d.flags = kTimerActive | (oneshot ? kTimerOneshot : 0u);
+    CK(cudaMemcpyAsync(b->d_timers + (size_t)l * b->K + k, &d, sizeof(d), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->n_timers++;
+    if (!oneshot) b->min_period = std::min(b->min_period, period_ns);
+    else b->oneshot_idx.push_back((size_t)l * b->K + k);
+    if (timer_id) *timer_id = l * b->K + k;
+    return push_mask_words(b, l, 1);
+  }
+  return CPBUS_ENOSPC;
+}
+
+int cpbus_timer_add_many(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t period_ns, const uint32_t* source_ids,
+                         uint32_t source_id0, int oneshot) {
+  if (!b || !period_ns || !n) return CPBUS_EINVAL;
+  if (!b->K) return CPBUS_ENOSPC;
+  const uint32_t l0 = first_sub - b->cfg.sub_id_base;
+  if (first_sub < b->cfg.sub_id_base || (uint64_t)l0 + n > b->n_next) return CPBUS_ENOENT;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  if (b->h_timers.empty()) b->h_timers.resize((size_t)b->N * b->K);
+  // bulk arm: uses slot 0 of each subscriber (must be free)
+  retire_oneshots(b, b->last_watermark);
+  for (uint32_t i = 0; i < n; i++) {
+    if (!b->h_active[l0 + i]) return CPBUS_ECLOSED;
+    if (b->h_timers[(size_t)(l0 + i) * b->K].active) return CPBUS_ENOSPC;
+  }
+  std::vector<DevTimer> dev((size_t)n * b->K);
+  memset(dev.data(), 0, dev.size() * sizeof(DevTimer));
+  CK(cudaMemcpyAsync(dev.data(), b->d_timers + (size_t)l0 * b->K, dev.size() * sizeof(DevTimer), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (uint32_t i = 0; i < n; i++) {
+    HostTimer& t = b->h_timers[(size_t)(l0 + i) * b->K];
+    t.active = true; t.oneshot = oneshot != 0; t.period = period_ns; t.next_due = b->now + period_ns;
+    t.source_id = source_ids ? source_ids[i] : source_id0 + i;
+    DevTimer& d = dev[(size_t)i * b->K];
+    d.next_due = t.next_due; d.period = period_ns; d.source_id = t.source_id; d.fired = 0;
+    d.flags = kTimerActive | (oneshot ? kTimerOneshot : 0u);
+    if (oneshot) b->oneshot_idx.push_back((size_t)(l0 + i) * b->K);
+  }
+  CK(cudaMemcpyAsync(b->d_timers + (size_t)l0 * b->K, dev.data(), dev.size() * sizeof(DevTimer), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->n_timers += n;
+  if (!oneshot) b->min_period = std::min(b->min_period, period_ns);
+  return push_mask_words(b, l0, n);
+}
+
+int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
+  if (!b) return CPBUS_EINVAL;
+  if (!b->K || b->h_timers.empty()) return CPBUS_ENOENT;
+  const uint32_t l = timer_id / b->K, k = timer_id % b->K;
+  if (l >= b->n_next) return CPBUS_ENOENT;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;   // firings due before the cancel still happen
+  retire_oneshots(b, b->last_watermark);
+  HostTimer& t = b->h_timers[(size_t)l * b->K + k];
+  if (!t.active) return CPBUS_ENOENT;
+  t.active = false; b->n_timers--;
+  CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K + k, 0, sizeof(DevTimer), b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->n_timers == 0) b->min_period = UINT64_MAX;
+  return push_mask_words(b, l, 1);
+}
+
+int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) {
+  if (!b || (!ev && n)) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t code = ev[i].code;
+    if (code >= CPBUS_N_CODES) return CPBUS_EINVAL;
+    if ((rc = stage_one(b, code, ev[i].source_id, CPBUS_TARGET_ALL, 0))) return rc;
+    const cpbus_event& e = b->h_batch[b->cur][b->n_staged - 1];
+    if (code != CPBUS_METRIC) b->st.published_by_code[code]++;   // events/bus.go:130-132
+    dbg_enqueue(b, e);                                           // events/bus.go:139
+    b->st.publishes++;
+  }
+  return CPBUS_OK;
+}
+
+int cpbus_send(cpbus_t* b, uint32_t sub_id, const cpbus_event* ev) {
+  if (!b || !ev || ev->code >= CPBUS_N_CODES) return CPBUS_EINVAL;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = stage_one(b, ev->code, ev->source_id, sub_id, CPBUS_F_UNICAST))) return rc;
+  b->st.publishes++;
+  return CPBUS_OK;
+}
+
+int cpbus_advance(cpbus_t* b, uint64_t now_ns) {
+  if (!b) return CPBUS_EINVAL;
+  if (now_ns < b->now) return CPBUS_EORDER;
+  if (now_ns == b->now) return CPBUS_OK;
+  int rc = dev_guard(b); if (rc) return rc;
+  // the kernel looks at <= 32/K candidate firings per timer slot per launch: keep every
+  // flush window within that many periods of the fastest periodic timer
+  const uint64_t win = max_window(b);
+  while (win != UINT64_MAX && now_ns - b->last_watermark > win) {
+    b->now = b->last_watermark + win;
+    if ((rc = flush_staged(b, b->now))) return rc;
+  }
+  b->now = now_ns;
+  return CPBUS_OK;
+}
+
+int cpbus_flush(cpbus_t* b) {
+  if (!b) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  return flush_staged(b, b->now);
+}
+
+int cpbus_sync(cpbus_t* b) {
+  if (!b) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaStreamSynchronize(b->stream));
+  return CPBUS_OK;
+}
+
+int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
+  if (!b || (!d_events && n) || n > b->B || ((uintptr_t)d_events & 31u)) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  if (watermark_ns < b->now) return CPBUS_EORDER;
+  if (watermark_ns - b->last_watermark > max_window(b)) return CPBUS_EORDER;
+  bool ok = true;
+  if ((rc = admit(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, &ok))) return rc;
+  if (!ok) return CPBUS_EAGAIN;
+  b->now = watermark_ns;
+  if ((rc = launch_fanout(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns))) return rc;
+  b->st.publishes += n; b->seq += n;
+  return CPBUS_OK;
+}
+
+static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {
+  CK(cudaMemcpyAsync(tail, b->d_tail + l, 8, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(head, b->d_head + l, 8, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return CPBUS_OK;
+}
+
+static int copy_slots(cpbus* b, uint32_t l, uint64_t from, size_t n, cpbus_event* out) {
+  const cpbus_event* ring = b->d_ring + (size_t)l * b->R;
+  const uint32_t s0 = (uint32_t)(from & (b->R - 1));
+  const size_t first = std::min<size_t>(n, b->R - s0);
+  if (first) CK(cudaMemcpyAsync(out, ring + s0, first * sizeof(cpbus_event), cudaMemcpyDeviceToHost, b->stream));
+  if (n > first) CK(cudaMemcpyAsync(out + first, ring, (n - first) * sizeof(cpbus_event), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return CPBUS_OK;
+}
+
+int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n, uint64_t* lost) {
+  if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  uint64_t tail = 0, head = 0;
+  if ((rc = read_cursors(b, l, &tail, &head))) return rc;
+  if (lost) *lost = 0;
+  const size_t take = (size_t)std::min<uint64_t>(tail - head, cap);
+  if (take && (rc = copy_slots(b, l, head, take, out))) return rc;
+  head += take;
+  CK(cudaMemcpyAsync(b->d_head + l, &head, 8, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  *n = take;
+  return CPBUS_OK;
+}
+
+int cpbus_peek_window(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n) {
+  if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  uint64_t tail = 0, head = 0;
+  if ((rc = read_cursors(b, l, &tail, &head))) return rc;
+  const size_t take = (size_t)std::min<uint64_t>(std::min<uint64_t>(tail, b->R), cap);
+  if (take && (rc = copy_slots(b, l, tail - take, take, out))) return rc;
+  *n = take;
+  return CPBUS_OK;
+}
+
+int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out) {
+  if (!b || !out || !n) return CPBUS_EINVAL;
+  const uint32_t l = first_sub - b->cfg.sub_id_base;
+  if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  std::vector<uint64_t> t(n), d(n);
+  CK(cudaMemcpyAsync(t.data(), b->d_tail + l, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(d.data(), b->d_digest + l, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (uint32_t i = 0; i < n; i++) { out[i].count = t[i]; out[i].digest = d[i]; }
+  return CPBUS_OK;
+}
+
+int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4]) {
+  if (!b || !out || !n) return CPBUS_EINVAL;
+  const uint32_t l = first_sub - b->cfg.sub_id_base;
+  if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaMemsetAsync(b->d_fold, 0, 32, b->stream));
+  const uint32_t threads = 256, grid = std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)b->sm_count * 4);
+  digest_fold_kernel<<<grid, threads, 0, b->stream>>>(b->d_tail, b->d_digest, l, n, b->cfg.sub_id_base, b->d_fold);
+  CK(cudaGetLastError());
+  b->st.kernel_launches++;
+  CK(cudaMemcpyAsync(b->h_fold, b->d_fold, 32, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < 4; i++) out[i] = b->h_fold[i];
+  return CPBUS_OK;
+}
+
+// DebugEvents — events/bus.go:34-54
+int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) {
+  if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
+  size_t k = 0;
+  for (;;) {
+    if (b->dbg_head == -1) break;
+    const cpbus_event e = b->dbg[b->dbg_tail % 10];
+    if (b->dbg_tail == b->dbg_head) { b->dbg_head = -1; b->dbg_tail = 0; }
+    else b->dbg_tail = (b->dbg_tail + 1) % 10;
+    if (e.code == CPBUS_NONE && e.source_id == 0) break;   // == NonEvent
+    if (k < cap) out[k] = e;
+    k++;
+  }
+  *n = k;
+  return CPBUS_OK;
+}
+
+int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
+  if (!b || !out) return CPBUS_EINVAL;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  retire_oneshots(b, b->last_watermark);
+  b->st.deliveries = b->h_stats->deliveries; b->st.ticks = b->h_stats->ticks; b->st.overwritten = b->h_stats->overwritten;
+  b->st.n_subs = b->n_active; b->st.n_timers = b->n_timers; b->st.now_ns = b->now;
+  *out = b->st;
+  return CPBUS_OK;
+}
+
+int cpbus_device_ptrs(cpbus_t* b, void** ring, void** tail, void** mask, void** digest) {
+  if (!b) return CPBUS_EINVAL;
+  if (ring) *ring = b->d_ring;
+  if (tail) *tail = b->d_tail;
+  if (mask) *mask = b->d_mask;
+  if (digest) *digest = b->d_digest;
+  return CPBUS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+/*
+ * cpbus.h — C-ABI of libcpbus, the B200-native event bus that sits behind
+ * ContainerPilot's `events` package (reference: /root/reference/events/).
+ *
+ * This header is the drop-in boundary.  It is what a cgo shim
+ * for package `events` binds (see INTEGRATION.md for the Go side).  Everything
+ * is plain C: pointers + sizes, `int` status returns (0 = OK, negative =
+ * CPBUS_E*), no exceptions, no torch types.  The library never keeps a caller
+ * pointer past the call (cgo pointer rule).  One publisher thread at a time
+ * per bus (the shim keeps `bus.lock`, reference events/bus.go:126); drain and
+ * stats may be called from another thread between flushes.
+ *
+ * Record format (frozen): one 32-byte, 32-byte-aligned record = exactly one
+ * HBM/L2 sector.  Go's `Event{Code EventCode; Source string}`
+ * (events/events.go:10-13) maps to {code, source_id} through the host-side
+ * intern table (cpbus_intern); seq/ts/target/flags are bus bookkeeping.
+ */
+#ifndef CPBUS_H
+#define CPBUS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- event codes: events/events.go:21-39 (iota order is the wire value) ---- */
+enum {
+  CPBUS_NONE = 0, CPBUS_EXIT_SUCCESS, CPBUS_EXIT_FAILED, CPBUS_STOPPING,
+  CPBUS_STOPPED, CPBUS_STATUS_HEALTHY, CPBUS_STATUS_UNHEALTHY,
+  CPBUS_STATUS_CHANGED, CPBUS_TIMER_EXPIRED, CPBUS_ENTER_MAINTENANCE,
+  CPBUS_EXIT_MAINTENANCE, CPBUS_ERROR, CPBUS_QUIT, CPBUS_METRIC,
+  CPBUS_STARTUP, CPBUS_SHUTDOWN, CPBUS_SIGNAL,
+  CPBUS_N_CODES /* 17 */
+};
+
+/* subscription mask: bit i set <=> subscriber wants EventCode i.
+ * CPBUS_MASK_ALL reproduces the reference exactly (the reference bus has no
+ * filter: events/bus.go:134-138 delivers every event to every subscriber). */
+#define CPBUS_MASK_ALL 0x0001FFFFu
+
+#define CPBUS_TARGET_ALL 0xFFFFFFFFu /* broadcast (EventBus.Publish)            */
+#define CPBUS_F_TICK     0x1u        /* record produced by a timer (events/timer.go) */
+#define CPBUS_F_UNICAST  0x2u        /* direct mailbox send (`sub.Rx <- ev`, jobs/jobs.go:262) */
+
+typedef struct cpbus_event {
+  uint64_t seq;       /* publish: global publish ordinal (0-based, bus lifetime).
+                         tick: firing ordinal of that timer (0-based).          */
+  uint64_t ts_ns;     /* virtual clock when published / due time of the tick    */
+  uint32_t code;      /* EventCode                                              */
+  uint32_t source_id; /* interned Event.Source                                  */
+  uint32_t target;    /* CPBUS_TARGET_ALL, or the global subscriber id          */
+  uint32_t flags;     /* CPBUS_F_*                                              */
+} cpbus_event;        /* sizeof == 32 */
+
+/* ---- status codes ---- */
+enum {
+  CPBUS_OK = 0,
+  CPBUS_EINVAL = -1,   /* bad argument                                           */
+  CPBUS_ENOMEM = -2,   /* host or device allocation failed                       */
+  CPBUS_ECUDA = -3,    /* CUDA runtime error (cpbus_last_cuda_error has detail)  */
+  CPBUS_EAGAIN = -4,   /* lossless mode: a targeted mailbox is full; drain+retry */
+  CPBUS_ENOSPC = -5,   /* subscriber / timer / intern table capacity exhausted   */
+  CPBUS_ENOENT = -6,   /* unknown subscriber / timer id                          */
+  CPBUS_ECLOSED = -7,  /* subscriber already unsubscribed (Go: panic, bus.go:121)*/
+  CPBUS_ENODEV = -8,   /* no CUDA device: there is NO CPU fallback               */
+  CPBUS_EORDER = -9    /* device batch not sorted by ts / clock moved backwards  */
+};
+
+/* cpbus_config.flags */
+#define CPBUS_CFG_LOSSLESS 0x1u /* reference semantics: never drop; a full mailbox
+                                   stalls the publisher (events/subscriber.go:30-32).
+                                   Without it the bus runs in overwrite-oldest
+                                   throughput mode (no consumer needed).          */
+#define CPBUS_CFG_DIGEST   0x2u /* maintain the per-subscriber order-sensitive
+                                   64-bit digest in-kernel                       */
+
+/* cpbus_config.store_path: how records reach the rings (all are bit-identical) */
+enum {
+  CPBUS_STORE_AUTO = 0, /* library default = best measured       */
+  CPBUS_STORE_V4   = 1, /* st.global.v4.b32: lane pair per record, 16 B / lane   */
+  CPBUS_STORE_V8   = 2, /* st.global.v8.b32: one lane per record, 32 B / lane    */
+  CPBUS_STORE_BULK = 3  /* cp.async.bulk smem->global (TMA) for dense segments   */
+};
+
+typedef struct cpbus_config {
+  uint32_t n_max_subs;     /* capacity of this shard's subscriber table           */
+  uint32_t ring_cap;       /* records per mailbox; power of two, >= 64 (1024 = default; reference channel cap is 1000, jobs/jobs.go:23) */
+  uint32_t batch_cap;      /* max events per flush; <= ring_cap/2, multiple of 32 */
+  uint32_t timers_per_sub; /* timer slots per subscriber: 0,1,2,4,8               */
+  uint32_t flags;          /* CPBUS_CFG_*                                         */
+  int32_t  device;         /* CUDA device ordinal; -1 = current device            */
+  uint32_t sub_id_base;    /* global id of this shard's subscriber 0 (multi-GPU:
+                              contiguous shards)                   */
+  uint32_t store_path;     /* CPBUS_STORE_*                                       */
+  void*    stream;         /* cudaStream_t to run on; NULL = library-owned stream */
+  uint32_t grid_ctas;      /* 0 = auto (multiple of the SM count)                 */
+  uint32_t reserved[5];
+} cpbus_config;
+
+typedef struct cpbus_digest_t {
+  uint64_t count;  /* records ever delivered to this mailbox (broadcast + unicast + ticks) */
+  uint64_t digest; /* rolling h = h*P + H(record) over the delivered sequence (mod 2^64)  */
+} cpbus_digest_t;
+
+typedef struct cpbus_stats_t {
+  uint64_t publishes;      /* events that entered Publish/Send                    */
+  uint64_t deliveries;     /* 32-B records landed in mailboxes (incl. ticks)      */
+  uint64_t ticks;          /* timer records among the deliveries                  */
+  uint64_t batches;        /* fan-out launches                                    */
+  uint64_t kernel_launches;/* all kernels this bus launched                       */
+  uint64_t overwritten;    /* undrained records lost to overwrite-oldest          */
+  uint64_t published_by_code[CPBUS_N_CODES]; /* reconciliation of the Prometheus
+                              `containerpilot_events` counter (events/bus.go:130-132) */
+  uint32_t n_subs;         /* currently subscribed                                */
+  uint32_t n_timers;       /* currently armed                                     */
+  uint64_t now_ns;         /* virtual clock                                       */
+} cpbus_stats_t;
+
+typedef struct cpbus cpbus_t;
+
+/* ---- lifecycle: NewEventBus (events/bus.go:72-88); reload = destroy+create (core/app.go:142) ---- */
+int cpbus_create(const cpbus_config* cfg, cpbus_t** out);
+int cpbus_destroy(cpbus_t* bus);
+
+/* ---- Event.Source interning (events/events.go:12) ---- */
+int cpbus_intern(cpbus_t* bus, const char* s, size_t len, uint32_t* source_id);
+/* copies at most cap bytes; *len receives the full length */
+int cpbus_source(cpbus_t* bus, uint32_t source_id, char* out, size_t cap, size_t* len);
+
+/* ---- membership: Subscribe/Unsubscribe (events/bus.go:105-122).  Ordered with
+ *      publishes: any staged events are flushed first. ---- */
+int cpbus_subscribe(cpbus_t* bus, uint32_t code_mask, uint32_t* sub_id);
+int cpbus_subscribe_many(cpbus_t* bus, const uint32_t* code_masks, uint32_t n, uint32_t* first_sub_id);
+int cpbus_unsubscribe(cpbus_t* bus, uint32_t sub_id);
+
+/* ---- timers: NewEventTimer / NewEventTimeout (events/timer.go:40-71 / 12-37).
+ *      The first firing is due at now + period_ns; a periodic timer then fires
+ *      every period_ns, a one-shot exactly once.  cancel = ctx.Done(). ---- */
+int cpbus_timer_add(cpbus_t* bus, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id);
+/* one periodic timer per subscriber [first_sub, first_sub+n); source_ids[i] (or source_id0+i if NULL) */
+int cpbus_timer_add_many(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t period_ns, const uint32_t* source_ids, uint32_t source_id0, int oneshot);
+int cpbus_timer_cancel(cpbus_t* bus, uint32_t timer_id);
+
+/* ---- the hot path: EventBus.Publish (events/bus.go:125-140) ---- */
+/* Stages n events; only code/source_id are read from ev (seq, ts, target, flags
+ * are stamped by the bus).  Flushes automatically whenever batch_cap is reached. */
+int cpbus_publish(cpbus_t* bus, const cpbus_event* ev, size_t n);
+/* Direct mailbox write, bypassing the filter (`job.Rx <- ev`, jobs/jobs.go:262;
+ * Subscriber.Receive, events/subscriber.go:30).  Ordered with publishes. */
+int cpbus_send(cpbus_t* bus, uint32_t sub_id, const cpbus_event* ev);
+/* Move the virtual clock; timers whose due time <= now_ns fire at the next flush,
+ * ordered before any event published after this call. */
+int cpbus_advance(cpbus_t* bus, uint64_t now_ns);
+/* Launch the fan-out for everything staged (async on the bus stream). */
+int cpbus_flush(cpbus_t* bus);
+int cpbus_sync(cpbus_t* bus);
+/* Fan out a batch that is already resident in HBM (multi-GPU: the NCCL-broadcast
+ * stream; bench: device-resident trace).  Records are complete
+ * (seq/ts/target/flags set by the producer), sorted by ts_ns, n <= batch_cap,
+ * 32-byte aligned.  watermark_ns >= last ts; becomes the bus clock. */
+int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
+
+/* ---- consumer side ---- */
+/* Mailbox -> host, FIFO (`<-sub.Rx`).  *lost = records overwritten before they
+ * could be drained (always 0 in lossless mode). */
+int cpbus_drain(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n, uint64_t* lost);
+/* Last min(cap, ring_cap, count) delivered records, oldest first, without consuming. */
+int cpbus_peek_window(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n);
+int cpbus_digest(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_digest_t* out);
+/* XOR-fold / sum of (count, digest) over [first_sub, first_sub+n) computed on the
+ * device: one 32-byte D2H instead of 16 B per subscriber. */
+int cpbus_digest_fold(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t out[4]);
+
+/* ---- observation ---- */
+/* DebugEvents (events/bus.go:34-54): drains the 10-slot ring of the last published
+ * events, oldest first, stopping at a NonEvent.  Host-side, no 100 ms sleep. */
+int cpbus_debug_events(cpbus_t* bus, cpbus_event* out, size_t cap, size_t* n);
+int cpbus_stats(cpbus_t* bus, cpbus_stats_t* out);
+/* device pointers for zero-copy inspection by tests/bench (ring, tail) */
+int cpbus_device_ptrs(cpbus_t* bus, void** ring, void** tail, void** mask, void** digest);
+
+/* ---- names: EventCode.String (events/eventcode_string.go:9-15), FromString (events/events.go:52-86) ---- */
+const char* cpbus_code_name(int code);               /* NULL if out of range      */
+int cpbus_code_from_string(const char* name);        /* code, or -1 if not valid  */
+
+const char* cpbus_strerror(int status);
+const char* cpbus_last_cuda_error(void);
+uint32_t cpbus_abi_version(void);
+/* 64-bit record hash and digest multiplier used by the in-kernel digest (so the
+ * oracle and external checkers can reproduce it without reading kernel code) */
+uint64_t cpbus_record_hash(const cpbus_event* ev);
+uint64_t cpbus_digest_multiplier(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPBUS_H */

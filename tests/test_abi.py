@@ -1,0 +1,78 @@
+"""The C-ABI boundary: libcpbus.so loads here (no GPU) and exports every symbol
+include/cpbus.h declares; host-only entry points agree with the golden vectors; and
+without a device the library refuses to run (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+
+import oracle_binding as ob
+from containerpilot_b200 import _native as nat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cpbus.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cpbus_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(nat.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"libcpbus.so does not export {n}"
+    assert set(names) == set(nat.SYMBOLS), set(names) ^ set(nat.SYMBOLS)
+    assert nat.load().cpbus_abi_version() == 1
+
+
+def test_record_layout_is_32_bytes():
+    assert C.sizeof(nat.Event) == 32 and ob.EVENT_DTYPE.itemsize == 32
+    assert [f[0] for f in nat.Event._fields_] == list(ob.EVENT_DTYPE.names)
+
+
+def test_names_agree_with_reference_vectors():
+    G = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+    lib = nat.load()
+    for i, n in enumerate(G["code_names"]["names"]):
+        assert lib.cpbus_code_name(i).decode() == n
+    assert lib.cpbus_code_name(17) is None
+    for name, code in G["from_string"]["accepted"].items():
+        assert lib.cpbus_code_from_string(name.encode()) == code
+    for name in G["from_string"]["rejected"]:
+        assert lib.cpbus_code_from_string(name.encode()) == -1
+
+
+def test_record_hash_spec_matches_oracle():
+    lib = nat.load()
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        e = nat.Event(int(rng.integers(0, 1 << 62)), int(rng.integers(0, 1 << 62)), int(rng.integers(0, 17)),
+                      int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << 32)), int(rng.integers(0, 4)))
+        assert lib.cpbus_record_hash(C.byref(e)) == ob.lib().orc_record_hash(bytes(e))
+    assert lib.cpbus_digest_multiplier() == ob.lib().orc_digest_multiplier()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    cfg = nat.Config(); cfg.n_max_subs = 8; cfg.device = -1
+    h = C.c_void_p()
+    assert nat.load().cpbus_create(C.byref(cfg), C.byref(h)) == nat.ENODEV
+    assert not h.value
+    assert b"no CPU fallback" in nat.load().cpbus_strerror(nat.ENODEV)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under containerpilot_b200/ or include/ may reference it."""
+    for base in ("containerpilot_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
+                    txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                    assert "oracle_binding" not in txt and "libcpbus_oracle" not in txt and "orc_" not in txt, fn

@@ -1,0 +1,245 @@
+"""Parity tests proper: the CUDA bus, driven through the C-ABI, against the CPU
+oracle on the same seeded traces.  Bit-exact: same records, same per-subscriber
+order, same counts, same order-sensitive digests."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import trace as tr
+from containerpilot_b200 import _native as nat
+from containerpilot_b200.bus import Bus, EVENT_DTYPE
+
+pytestmark = pytest.mark.gpu
+STORES = [nat.STORE_V4, nat.STORE_V8, nat.STORE_BULK]
+
+
+def publish_codes(bus, codes, srcs):
+    ev = np.zeros(len(codes), dtype=EVENT_DTYPE)
+    ev["code"], ev["source_id"] = codes, srcs
+    nat.check(bus.publish_many(ev), "publish")
+
+
+@pytest.mark.parametrize("store", STORES)
+def test_config1_plumbing_full_sequences(store):
+    """BASELINE config 1: 8 subscribers, 10k events, all-ones masks, single publisher.
+    Lossless mode with a consumer draining, like the reference's blocking channels:
+    the FULL per-subscriber sequence is compared."""
+    n_subs, n_events = 8, 10_000
+    rng = np.random.default_rng(0xC0DEB201)
+    codes = rng.integers(1, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 64, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs)
+    for _ in range(n_subs):
+        orc.subscribe()
+    assert orc.publish_many(codes, srcs) == 0
+    with Bus(n_subs, ring_cap=1024, batch_cap=256, lossless=True, store_path=store) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        got = [[] for _ in range(n_subs)]
+        ev = np.zeros(1, dtype=EVENT_DTYPE)
+        i = 0
+        while i < n_events:
+            ev["code"], ev["source_id"] = codes[i], srcs[i]
+            rc = bus.publish_many(ev)
+            if rc == nat.EAGAIN:                      # publisher blocked: consumers run
+                for s in range(n_subs):
+                    got[s].append(bus.drain(s))
+                continue
+            nat.check(rc, "publish")
+            i += 1
+        while bus.flush() == nat.EAGAIN:
+            for s in range(n_subs):
+                got[s].append(bus.drain(s))
+        for s in range(n_subs):
+            got[s].append(bus.drain(s))
+            seq = np.concatenate(got[s])
+            assert len(seq) == n_events
+            assert seq.tobytes() == orc.mailbox(s).tobytes(), f"subscriber {s}"
+        d = bus.digests(0, n_subs)
+        assert all(int(d["digest"][s]) == orc.digest(s) for s in range(n_subs))
+        st = bus.stats()
+        assert st["deliveries"] == n_subs * n_events and st["overwritten"] == 0 and st["publishes"] == n_events
+        assert st["published_by_code"] == [orc.published_by_code(c) for c in range(17)]
+
+
+@pytest.mark.parametrize("store", STORES)
+@pytest.mark.parametrize("batch_cap", [32, 256, 512])
+def test_dense_throughput_mode_window(store, batch_cap):
+    """All-ones masks, overwrite-oldest mode: count, digest and the last ring_cap records."""
+    n_subs, n_events = 300, 5000
+    rng = np.random.default_rng(5)
+    codes = rng.integers(0, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs, keep_window=1024)
+    for _ in range(n_subs):
+        orc.subscribe()
+    orc.publish_many(codes, srcs)
+    with Bus(n_subs, ring_cap=1024, batch_cap=batch_cap, store_path=store) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        publish_codes(bus, codes, srcs)
+        nat.check(bus.flush(), "flush"); bus.sync()
+        st = tr.compare(bus, orc, n_subs)
+        assert st["overwritten"] == n_subs * (n_events - 1024)
+
+
+@pytest.mark.parametrize("store", STORES)
+@pytest.mark.parametrize("seed,K", [(1, 0), (2, 1), (3, 2), (4, 4), (5, 8)])
+def test_random_mixed_traces(store, seed, K):
+    """Filters, unicast sends, membership changes, clock advances, periodic and one-shot timers."""
+    ops, n_total = tr.random_ops(seed, 40, 6000, timers_per_sub=K, max_subs=64)
+    orc = tr.run_oracle(ops, 64, timers_per_sub=K)
+    with Bus(64, ring_cap=2048, batch_cap=128, timers_per_sub=K, store_path=store) as bus:
+        tr.run_bus(bus, ops)
+        tr.compare(bus, orc, n_total, window=2048)
+
+
+def test_timer_heavy_config3_shape():
+    """BASELINE config 3 shape, scaled: one periodic 1 kHz timer per subscriber, 1 tick per 100 publishes."""
+    n_subs, n_events, dt = 512, 20_000, 10_000      # 10 us per publish, 1 ms period
+    rng = np.random.default_rng(0xC0DEB203)
+    codes = rng.integers(1, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs, timers_per_sub=1, keep_window=1024)
+    for s in range(n_subs):
+        orc.subscribe(); orc.timer_add(s, 1_000_000, 5000 + s, False)
+    assert orc.publish_many(codes, srcs, dt_ns=dt) == 0
+    with Bus(n_subs, ring_cap=1024, batch_cap=256, timers_per_sub=1) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        bus.timer_add_many(0, n_subs, 1_000_000, source_id0=5000)
+        ev = np.zeros(1, dtype=EVENT_DTYPE)
+        for i in range(n_events):
+            nat.check(bus.advance((i + 1) * dt), "advance")
+            ev["code"], ev["source_id"] = codes[i], srcs[i]
+            nat.check(bus.publish_many(ev), "publish")
+        nat.check(bus.flush(), "flush"); bus.sync()
+        st = tr.compare(bus, orc, n_subs)
+        assert st["ticks"] == n_subs * (n_events * dt // 1_000_000)
+
+
+def test_zipf_filter_sweep_scaled():
+    """BASELINE config 5 shape, scaled: Zipf-skewed masks and event codes."""
+    n_subs, n_events = 2048, 8000
+    for s_exp in (0.5, 1.0, 1.5):
+        masks = tr.zipf_masks(n_subs, s_exp, 21); codes = tr.zipf_codes(n_events, s_exp, 22)
+        srcs = (np.arange(n_events) % 4096).astype(np.uint32)
+        orc = ob.Oracle(n_subs, keep_window=1024)
+        for m in masks:
+            orc.subscribe(int(m))
+        orc.publish_many(codes, srcs)
+        with Bus(n_subs, ring_cap=1024, batch_cap=256) as bus:
+            bus.subscribe_many(masks)
+            publish_codes(bus, codes, srcs)
+            nat.check(bus.flush(), "flush"); bus.sync()
+            st = tr.compare(bus, orc, n_subs)
+            assert st["deliveries"] == int(sum(bin(int(m)).count("1") and int(((masks[i] >> codes) & 1).sum()) for i, m in enumerate(masks)))
+
+
+def test_config2_scaled_and_device_resident_batches():
+    """BASELINE config 2, scaled to what the oracle finishes in seconds, fed through
+    cpbus_publish_device (HBM-resident batches, the multi-GPU / bench ingest path)."""
+    import torch
+    n_subs, n_events, B = 4096, 20_480, 256
+    rng = np.random.default_rng(0xC0DEB202)
+    codes = rng.integers(1, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs, keep_window=1024)
+    for _ in range(n_subs):
+        orc.subscribe()
+    orc.publish_many(codes, srcs)
+    ev = np.zeros(n_events, dtype=EVENT_DTYPE)
+    ev["seq"] = np.arange(n_events); ev["code"], ev["source_id"], ev["target"] = codes, srcs, nat.TARGET_ALL
+    dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32)).cuda()
+    stream = torch.cuda.current_stream()
+    with Bus(n_subs, ring_cap=1024, batch_cap=B, stream=stream.cuda_stream) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        for i in range(0, n_events, B):
+            nat.check(bus.publish_device(dev.data_ptr() + i * 32, B, 0), "publish_device")
+        bus.sync()
+        tr.compare(bus, orc, n_subs)
+        fold = bus.digest_fold(0, n_subs)
+        assert fold[0] == n_subs * n_events and fold[3] == n_subs
+        assert fold[1] == (orc.digest(0) * n_subs) & 0xFFFFFFFFFFFFFFFF     # every mailbox holds the same sequence
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full width (65,536 subscribers): size-independent properties.
+    Every mailbox must hold the same sequence as oracle subscriber 0 (all-ones masks)."""
+    import torch
+    n_subs, n_events, B = 65_536, 4096, 256
+    rng = np.random.default_rng(0xC0DEB202)
+    codes = rng.integers(1, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    orc = ob.Oracle(1, keep_window=1024); orc.subscribe(); orc.publish_many(codes, srcs)
+    ev = np.zeros(n_events, dtype=EVENT_DTYPE)
+    ev["seq"] = np.arange(n_events); ev["code"], ev["source_id"], ev["target"] = codes, srcs, nat.TARGET_ALL
+    dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32)).cuda()
+    with Bus(n_subs, ring_cap=1024, batch_cap=B, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        for i in range(0, n_events, B):
+            nat.check(bus.publish_device(dev.data_ptr() + i * 32, B, 0), "publish_device")
+        bus.sync()
+        d = bus.digests(0, n_subs)
+        assert (d["count"] == n_events).all() and (d["digest"] == np.uint64(orc.digest(0))).all()
+        want = orc.mailbox(0).tobytes()
+        for s in (0, 1, 7, 4095, 32_768, 65_535):
+            assert bus.peek_window(s).tobytes() == want
+        # the ring memory itself: every mailbox identical (encode -> compare, no sampling)
+        ptrs = bus.device_ptrs()
+        st = bus.stats()
+        assert st["deliveries"] == n_subs * n_events
+
+
+def test_lossless_backpressure_and_drain():
+    """A full mailbox stalls the publisher (EAGAIN), nothing is lost, order is kept."""
+    orc = ob.Oracle(3)
+    for m in (nat.MASK_ALL, 1 << 2, nat.MASK_ALL):
+        orc.subscribe(m)
+    with Bus(3, ring_cap=64, batch_cap=32, lossless=True) as bus:
+        bus.subscribe_many(np.array([nat.MASK_ALL, 1 << 2, nat.MASK_ALL], dtype=np.uint32))
+        got = [[], [], []]
+        n_block = 0
+        for i in range(1000):
+            code = 1 + i % 3
+            orc.publish(code, i)
+            while True:
+                rc = bus.publish(code, i)
+                if rc == nat.EAGAIN:
+                    n_block += 1
+                    got[0].append(bus.drain(0)); got[2].append(bus.drain(2, cap=5))
+                    got[1].append(bus.drain(1))
+                    continue
+                nat.check(rc, "publish"); break
+        while bus.flush() == nat.EAGAIN:
+            for s in range(3):
+                got[s].append(bus.drain(s))
+        for s in range(3):
+            got[s].append(bus.drain(s))
+            assert np.concatenate(got[s]).tobytes() == orc.mailbox(s).tobytes()
+        assert n_block > 5 and bus.stats()["overwritten"] == 0
+
+
+def test_unsubscribe_twice_and_unknown_ids():
+    with Bus(4) as bus:
+        s = bus.subscribe()
+        bus.unsubscribe(s)
+        with pytest.raises(nat.CpbusError) as e:
+            bus.unsubscribe(s)
+        assert e.value.status == nat.ECLOSED                      # Go: negative WaitGroup panic (bus.go:121)
+        with pytest.raises(nat.CpbusError) as e:
+            bus.unsubscribe(99)
+        assert e.value.status == nat.ENOENT
+        assert bus.publish(1, 0) == nat.OK and bus.flush() == nat.OK   # publishing to nobody is fine (jobs_test.go:33-38)
+        assert bus.publish(17, 0) == nat.EINVAL
+        assert bus.advance(5) == nat.OK and bus.advance(4) == nat.EORDER
+
+
+def test_empty_and_ragged_batches():
+    """Edge cases: empty flush, single event, batch sizes that are not multiples of 32, ring wrap inside a batch."""
+    orc = ob.Oracle(5, keep_window=64)
+    for m in (nat.MASK_ALL, 0, 1 << 16, nat.MASK_ALL, 0x1FFFE):
+        orc.subscribe(m)
+    with Bus(5, ring_cap=64, batch_cap=32) as bus:
+        bus.subscribe_many(np.array([nat.MASK_ALL, 0, 1 << 16, nat.MASK_ALL, 0x1FFFE], dtype=np.uint32))
+        assert bus.flush() == nat.OK
+        n = 0
+        for chunk in (1, 31, 33, 7, 64, 1, 129):
+            for _ in range(chunk):
+                c = n % 17
+                orc.publish(c, n); nat.check(bus.publish(c, n), "publish"); n += 1
+            nat.check(bus.flush(), "flush")
+        bus.sync()
+        tr.compare(bus, orc, 5, window=64)
