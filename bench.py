@@ -226,9 +226,13 @@ def main():
     CHUNK = 64                                                         # batches per NCCL broadcast (512 KiB)
     state = {"step": 0}
 
-    def run_steps(k: int):
+    chunk_events = []                                                  # CPBUS_BENCH_TRACE=1: per-1000-step device timing
+
+    def run_steps(k: int, trace_chunks: bool = False):
         """k fan-out steps from the HBM-resident trace (multi-GPU: NCCL broadcast of the event stream)."""
-        for _ in range(k):
+        for j in range(k):
+            if trace_chunks and j % 1000 == 0:
+                ev_ = torch.cuda.Event(enable_timing=True); ev_.record(stream); chunk_events.append((j, ev_, time.perf_counter()))
             i = state["step"]
             slot, cycle = i % n_trace_batches, i // n_trace_batches
             if slot == 0 and cycle > 0:
@@ -254,11 +258,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    run_steps(steps)
+    run_steps(steps, trace_chunks=bool(os.environ.get("CPBUS_BENCH_TRACE")))
     e1.record(stream)
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
+    if chunk_events and rank == 0:
+        print("per-chunk device us/step:", [round(a[1].elapsed_time(b[1]) / (b[0] - a[0]) * 1e3, 1) for a, b in zip(chunk_events, chunk_events[1:])], file=sys.stderr)
+        print("per-chunk host us/step:", [round((b[2] - a[2]) / (b[0] - a[0]) * 1e6, 1) for a, b in zip(chunk_events, chunk_events[1:])], file=sys.stderr)
     st1 = bus.stats()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

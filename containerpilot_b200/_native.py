@@ -76,7 +76,7 @@ SYMBOLS = {
     "cpbus_digest_fold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64 * 4)]),
     "cpbus_debug_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_stats": (C.c_int, [C.c_void_p, _P(Stats)]),
-    "cpbus_device_ptrs": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p)]),
+    "cpbus_device_ptrs": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_void_p)]),
     "cpbus_code_name": (C.c_char_p, [C.c_int]),
     "cpbus_code_from_string": (C.c_int, [C.c_char_p]),
     "cpbus_strerror": (C.c_char_p, [C.c_int]),

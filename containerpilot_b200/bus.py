@@ -158,6 +158,6 @@ class Bus:
         return d
 
     def device_ptrs(self) -> dict:
-        ring, tail, mask, dig = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        nat.check(self._lib.cpbus_device_ptrs(self._h, C.byref(ring), C.byref(tail), C.byref(mask), C.byref(dig)), "cpbus_device_ptrs")
-        return {"ring": ring.value, "tail": tail.value, "mask": mask.value, "digest": dig.value}
+        ring, ctl = C.c_void_p(), C.c_void_p()
+        nat.check(self._lib.cpbus_device_ptrs(self._h, C.byref(ring), C.byref(ctl)), "cpbus_device_ptrs")
+        return {"ring": ring.value, "ctl": ctl.value}

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -47,10 +48,14 @@ struct cpbus {
 
   // HBM-resident state (SoA, one entry per subscriber of this shard)
   cpbus_event* d_ring = nullptr;          // N * R records: each mailbox is one contiguous 32*R-byte ring
-  unsigned long long *d_tail = nullptr, *d_head = nullptr, *d_digest = nullptr;
-  uint32_t* d_mask = nullptr;
+  SubCtl* d_ctl = nullptr;                // N control blocks: {tail, head, digest, mask}, one sector each
   DevTimer* d_timers = nullptr;           // N * K
   DevStats* d_stats = nullptr;
+  uint64_t* d_pow = nullptr;              // P^0..: digest multiplier powers, TMA-loaded by every CTA
+  unsigned char* d_desc = nullptr;        // per-launch batch descriptor (CTA 0 writes, the others read)
+  unsigned long long* d_desc_ready = nullptr;
+  unsigned long long launch_seq = 0;
+  uint32_t subs_per_warp = 0;             // 0 = auto
   unsigned long long* d_fold = nullptr;   // 4 words
   cpbus_event* d_batch[2] = {nullptr, nullptr};
   cpbus_event* h_batch[2] = {nullptr, nullptr};   // pinned staging
@@ -63,6 +68,7 @@ struct cpbus {
   // registry mirror (events/bus.go:13 `registry map[*Subscriber]bool`)
   std::vector<uint32_t> h_mask;
   std::vector<uint8_t> h_active;
+  std::vector<uint64_t> h_drained;        // consumer cursor as the host last left it (to report overwritten records)
   std::vector<size_t> oneshot_idx;        // armed one-shot timers (index into h_timers)
   std::vector<HostTimer> h_timers;        // N*K, allocated on first timer
   uint32_t n_next = 0, n_active = 0, n_timers = 0;
@@ -109,9 +115,28 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
 template <int STORE>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done = false;   // per instantiation
+  static size_t occ_smem = ~(size_t)0;
+  static int occ_blocks = 1;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(fanout_kernel<STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
+  }
+  if (!grid) {
+    // Several waves of short-lived CTAs rather than one persistent wave: the hardware CTA scheduler
+    // balances the two dies / SM speed spread for free (pure-store microbenchmark, scripts/write_ceiling.cu:
+    // 6.0 TB/s with one resident wave, 6.9 TB/s with >= 32 CTAs per SM).  Per-CTA setup here is a descriptor
+    // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is ~14 CTAs per SM
+    // (65,536 subscribers: 4 per warp -> 88.5 % of peak vs 83.3 % persistent, 75.7 % at 1 per warp).
+    if (occ_smem != smem) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE>, kThreads, smem));
+      occ_smem = smem;
+      if (occ_blocks < 1) occ_blocks = 1;
+    }
+    const uint32_t need = (p.n_subs + kWarpsPerCta - 1) / kWarpsPerCta;
+    uint32_t spw = b->subs_per_warp;
+    if (!spw) spw = std::max(1u, need / (uint32_t)(b->sm_count * 14));
+    grid = std::max(1u, std::min((need + spw - 1) / spw, need));
+    (void)occ_blocks;
   }
   fanout_kernel<STORE><<<grid, kThreads, smem, b->stream>>>(p);
   CK(cudaGetLastError());
@@ -123,20 +148,13 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
-  p.batch = d_src; p.ring = b->d_ring; p.tail = b->d_tail; p.head = b->d_head; p.digest = b->d_digest;
-  p.mask = b->d_mask; p.timers = b->d_timers; p.stats = b->d_stats; p.w_now = w; p.n_ev = n;
+  p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
   const size_t smem = fanout_smem_bytes(p.smem_cap);
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
-  uint32_t grid = b->cfg.grid_ctas;
-  if (!grid) {
-    // persistent-style grid: a multiple of the SM count, as many CTAs per SM as shared memory allows (<= 4)
-    uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 1024)));
-    grid = (uint32_t)b->sm_count * per_sm;
-  }
-  grid = std::max(1u, std::min(grid, need));
+  uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
   switch (b->store) {
     case CPBUS_STORE_V4: rc = launch_fanout_t<CPBUS_STORE_V4>(b, p, grid, smem); break;
@@ -155,8 +173,8 @@ int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) 
   if (!b->lossless || b->n_next == 0) return CPBUS_OK;
   CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, sizeof(unsigned long long), b->stream));
   const uint32_t threads = 256, grid = (b->n_next + threads - 1) / threads;
-  admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_mask, b->d_tail, b->d_head, b->d_timers, b->n_next,
-                                                b->R, b->K, b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats);
+  admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_ctl, b->d_timers, b->n_next, b->R, b->K,
+                                                b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats);
   CK(cudaGetLastError());
   b->st.kernel_launches++;
   CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, sizeof(unsigned long long),
@@ -284,6 +302,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
   int rc = CPBUS_OK;
   auto fail = [&](int code) { cpbus_destroy(b); return code; };
   if (cfg->device >= 0) b->device = cfg->device;
@@ -304,9 +323,11 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     return fail(CPBUS_ENOMEM);                                                                \
   }
   ALLOC(b->d_ring, N * R * sizeof(cpbus_event));
-  ALLOC(b->d_tail, N * 8); ALLOC(b->d_head, N * 8); ALLOC(b->d_digest, N * 8); ALLOC(b->d_mask, N * 4);
+  ALLOC(b->d_ctl, N * sizeof(SubCtl));
   if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
-  ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32);
+  ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32); ALLOC(b->d_pow, kPowTableLen * 8);
+  ALLOC(b->d_desc, fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 128);
+  if (cudaMemsetAsync(b->d_desc_ready, 0, 128, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   for (int i = 0; i < 2; i++) {
     ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));
     if (cudaMallocHost((void**)&b->h_batch[i], (size_t)B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -316,16 +337,21 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   if (cudaMallocHost((void**)&b->h_stats, sizeof(DevStats)) != cudaSuccess) return fail(CPBUS_ENOMEM);
   if (cudaMallocHost((void**)&b->h_fold, 32) != cudaSuccess) return fail(CPBUS_ENOMEM);
   // rings are NOT cleared: a slot is only ever read after it has been written (head/tail bound every read)
-  bool ok = cudaMemsetAsync(b->d_tail, 0, N * 8, b->stream) == cudaSuccess &&
-            cudaMemsetAsync(b->d_head, 0, N * 8, b->stream) == cudaSuccess &&
-            cudaMemsetAsync(b->d_digest, 0, N * 8, b->stream) == cudaSuccess &&
-            cudaMemsetAsync(b->d_mask, 0, N * 4, b->stream) == cudaSuccess &&
+  bool ok = cudaMemsetAsync(b->d_ctl, 0, N * sizeof(SubCtl), b->stream) == cudaSuccess &&
             cudaMemsetAsync(b->d_stats, 0, sizeof(DevStats), b->stream) == cudaSuccess &&
             (!K || cudaMemsetAsync(b->d_timers, 0, N * K * sizeof(DevTimer), b->stream) == cudaSuccess) &&
             cudaStreamSynchronize(b->stream) == cudaSuccess;
   if (!ok) return fail(CPBUS_ECUDA);
+  {
+    std::vector<uint64_t> pw(kPowTableLen);
+    uint64_t x = 1;
+    for (uint32_t i = 0; i < kPowTableLen; i++) { pw[i] = x; x *= kDigestP; }
+    if (cudaMemcpyAsync(b->d_pow, pw.data(), kPowTableLen * 8, cudaMemcpyHostToDevice, b->stream) != cudaSuccess ||
+        cudaStreamSynchronize(b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
+  }
   b->h_mask.assign(N, 0);
   b->h_active.assign(N, 0);
+  b->h_drained.assign(N, 0);
   b->intern.emplace(std::string(), 0u);   // "" -> 0 so that NonEvent == {None, 0} (events/events.go:45)
   b->sources.emplace_back();
   *out = b;
@@ -336,8 +362,8 @@ int cpbus_destroy(cpbus_t* b) {
   if (!b) return CPBUS_EINVAL;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->d_ring); cudaFree(b->d_tail); cudaFree(b->d_head); cudaFree(b->d_digest); cudaFree(b->d_mask);
-  cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold);
+  cudaFree(b->d_ring); cudaFree(b->d_ctl);
+  cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
   for (int i = 0; i < 2; i++) {
     cudaFree(b->d_batch[i]);
     if (b->h_batch[i]) cudaFreeHost(b->h_batch[i]);
@@ -377,13 +403,14 @@ int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = flush_staged(b, b->now))) return rc;   // ordered with publishes (events/bus.go:105-107 takes the same lock)
   const uint32_t first = b->n_next;
-  std::vector<uint32_t> words(n);
+  std::vector<SubCtl> blocks(n);
+  memset(blocks.data(), 0, (size_t)n * sizeof(SubCtl));
   for (uint32_t i = 0; i < n; i++) {
     b->h_mask[first + i] = (masks ? masks[i] : CPBUS_MASK_ALL) & CPBUS_MASK_ALL;
-    words[i] = b->h_mask[first + i] | kActiveBit;
+    blocks[i].mask = b->h_mask[first + i] | kActiveBit;
     b->h_active[first + i] = 1;
   }
-  CK(cudaMemcpyAsync(b->d_mask + first, words.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->d_ctl + first, blocks.data(), (size_t)n * sizeof(SubCtl), cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   b->n_next += n; b->n_active += n;
   if (first_sub_id) *first_sub_id = b->cfg.sub_id_base + first;
@@ -402,7 +429,7 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   if (!b->h_active[l]) return CPBUS_ECLOSED;
   b->h_active[l] = 0;
   const uint32_t word = 0;
-  CK(cudaMemcpyAsync(b->d_mask + l, &word, 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(&b->d_ctl[l].mask, &word, 4, cudaMemcpyHostToDevice, b->stream));
   if (b->K && !b->h_timers.empty()) {
     for (uint32_t k = 0; k < b->K; k++) {
       HostTimer& t = b->h_timers[(size_t)l * b->K + k];
@@ -418,7 +445,7 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
 static int push_mask_words(cpbus* b, uint32_t first, uint32_t n) {
   std::vector<uint32_t> words(n);
   for (uint32_t i = 0; i < n; i++) words[i] = mask_word(b, first + i);
-  CK(cudaMemcpyAsync(b->d_mask + first, words.data(), (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpy2DAsync(&b->d_ctl[first].mask, sizeof(SubCtl), words.data(), 4, 4, n, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   return CPBUS_OK;
 }
@@ -572,9 +599,10 @@ int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t wa
 }
 
 static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {
-  CK(cudaMemcpyAsync(tail, b->d_tail + l, 8, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaMemcpyAsync(head, b->d_head + l, 8, cudaMemcpyDeviceToHost, b->stream));
+  SubCtl c{};
+  CK(cudaMemcpyAsync(&c, b->d_ctl + l, sizeof(SubCtl), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
+  *tail = c.tail; *head = c.head;
   return CPBUS_OK;
 }
 
@@ -596,11 +624,12 @@ int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_
   int rc = dev_guard(b); if (rc) return rc;
   uint64_t tail = 0, head = 0;
   if ((rc = read_cursors(b, l, &tail, &head))) return rc;
-  if (lost) *lost = 0;
+  if (lost) { *lost = head - b->h_drained[l]; }
   const size_t take = (size_t)std::min<uint64_t>(tail - head, cap);
   if (take && (rc = copy_slots(b, l, head, take, out))) return rc;
   head += take;
-  CK(cudaMemcpyAsync(b->d_head + l, &head, 8, cudaMemcpyHostToDevice, b->stream));
+  b->h_drained[l] = head;
+  CK(cudaMemcpyAsync(&b->d_ctl[l].head, &head, 8, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *n = take;
   return CPBUS_OK;
@@ -626,11 +655,10 @@ int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out
   if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
-  std::vector<uint64_t> t(n), d(n);
-  CK(cudaMemcpyAsync(t.data(), b->d_tail + l, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaMemcpyAsync(d.data(), b->d_digest + l, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
+  std::vector<SubCtl> c(n);
+  CK(cudaMemcpyAsync(c.data(), b->d_ctl + l, (size_t)n * sizeof(SubCtl), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
-  for (uint32_t i = 0; i < n; i++) { out[i].count = t[i]; out[i].digest = d[i]; }
+  for (uint32_t i = 0; i < n; i++) { out[i].count = c[i].tail; out[i].digest = c[i].digest; }
   return CPBUS_OK;
 }
 
@@ -642,7 +670,7 @@ int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaMemsetAsync(b->d_fold, 0, 32, b->stream));
   const uint32_t threads = 256, grid = std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)b->sm_count * 4);
-  digest_fold_kernel<<<grid, threads, 0, b->stream>>>(b->d_tail, b->d_digest, l, n, b->cfg.sub_id_base, b->d_fold);
+  digest_fold_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, l, n, b->cfg.sub_id_base, b->d_fold);
   CK(cudaGetLastError());
   b->st.kernel_launches++;
   CK(cudaMemcpyAsync(b->h_fold, b->d_fold, 32, cudaMemcpyDeviceToHost, b->stream));
@@ -675,18 +703,20 @@ int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
   CK(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   retire_oneshots(b, b->last_watermark);
-  b->st.deliveries = b->h_stats->deliveries; b->st.ticks = b->h_stats->ticks; b->st.overwritten = b->h_stats->overwritten;
+  b->st.deliveries = b->st.ticks = b->st.overwritten = 0;
+  for (int i = 0; i < kStatSlots; i++) {
+    b->st.deliveries += b->h_stats->slot[i].deliveries; b->st.ticks += b->h_stats->slot[i].ticks;
+    b->st.overwritten += b->h_stats->slot[i].overwritten;
+  }
   b->st.n_subs = b->n_active; b->st.n_timers = b->n_timers; b->st.now_ns = b->now;
   *out = b->st;
   return CPBUS_OK;
 }
 
-int cpbus_device_ptrs(cpbus_t* b, void** ring, void** tail, void** mask, void** digest) {
+int cpbus_device_ptrs(cpbus_t* b, void** ring, void** ctl) {
   if (!b) return CPBUS_EINVAL;
   if (ring) *ring = b->d_ring;
-  if (tail) *tail = b->d_tail;
-  if (mask) *mask = b->d_mask;
-  if (digest) *digest = b->d_digest;
+  if (ctl) *ctl = b->d_ctl;
   return CPBUS_OK;
 }
 

@@ -22,10 +22,14 @@ namespace cpbus_dev {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef CPBUS_MIN_CTAS_PER_SM
+#define CPBUS_MIN_CTAS_PER_SM 3   // 80 registers/thread, no spills; 24 resident warps per SM
+#endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
 constexpr uint32_t kTimerActive = 1u, kTimerOneshot = 2u;
 constexpr uint64_t kDigestP = 0x9E3779B97F4A7C15ull;
+constexpr uint32_t kPowTableLen = 2048 + 65 + 7;   // batch_cap <= 2048
 
 struct __align__(32) DevTimer {     // one timer slot (events/timer.go: one goroutine + ticker)
   uint64_t next_due;
@@ -36,19 +40,35 @@ struct __align__(32) DevTimer {     // one timer slot (events/timer.go: one goro
   uint32_t pad;
 };
 
+// Statistics are spread over kStatSlots sector-sized slots: same-address REDs serialise at
+// L2 (~2.7 ns each, measured: 65,536 warps -> +180 us per launch), distinct sectors do not.
+constexpr int kStatSlots = 256;
+struct __align__(32) DevStatSlot { unsigned long long deliveries, ticks, overwritten, pad; };
 struct DevStats {
-  unsigned long long deliveries, ticks, overwritten, admit_overflow;
+  DevStatSlot slot[kStatSlots];
+  unsigned long long admit_overflow, pad[3];
+};
+
+// Per-subscriber control block: exactly one 32-byte sector, read once and written once
+// per subscriber per launch (the reference's hchan header: qcount/sendx/recvx, runtime/chan.go).
+struct __align__(32) SubCtl {
+  unsigned long long tail;    // records ever delivered to this mailbox
+  unsigned long long head;    // consumer cursor (records ever drained / overwritten)
+  unsigned long long digest;  // rolling order-sensitive digest of the delivered sequence
+  uint32_t mask;              // code mask | timer hint << 24 | active bit 31
+  uint32_t pad;
 };
 
 struct FanoutParams {
   const cpbus_event* batch;   // n_ev records, sorted by ts (HBM)
   cpbus_event* ring;          // [n_subs][R]
-  unsigned long long* tail;   // records ever delivered, per subscriber
-  unsigned long long* head;   // consumer cursor
-  unsigned long long* digest;
-  const uint32_t* mask;
+  SubCtl* ctl;                // [n_subs]
   DevTimer* timers;           // [n_subs][K] or nullptr
   DevStats* stats;
+  const uint64_t* pow_table;  // P^0 .. P^(kPowTableLen-1), computed once at cpbus_create
+  unsigned char* desc;        // per-launch batch descriptor, written by CTA 0, read by every other CTA
+  unsigned long long* desc_ready;   // holds the launch_seq whose descriptor is complete
+  unsigned long long launch_seq;
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -139,113 +159,174 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 //   [0, 32cap)            staged batch (TMA destination)
 //   [32cap, 40cap)        record hashes H(e_i)
 //   [40cap, 48cap)        {codebit, target} per event
-//   [48cap, 56cap + 520)  powers of the digest multiplier P^0 .. P^(cap+64)
-//   then                  mbarrier, batch summary, per-warp tick scratch
+//   [48cap, 56cap+8)      Q[i] = sum_{j<i} H(e_j) P^(n-1-j): prefix sums for O(#ticks) digests of dense runs
+//   then                  powers P^0 .. P^(cap+64), batch summary, per-warp tick scratch
 struct BatchSummary {
   uint64_t mbar;
-  uint64_t hfull;          // digest of the whole batch taken as one dense run
   uint32_t present;        // OR of codebits of the broadcast events
   uint32_t has_unicast;    // any record with a specific target
+  uint32_t hist[32];       // broadcast events per code
   uint64_t red[kWarpsPerCta];
 };
 
+__host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 34 * 4 + 8; }
+
 __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
-  return (size_t)cap * 56 + (64 + 1) * 8 + sizeof(BatchSummary) + kWarpsPerCta * 32 * sizeof(uint32_t) + 128;
+  return (size_t)cap * 56 + 16 + (size_t)(cap + 66) * 8 + sizeof(BatchSummary) + kWarpsPerCta * 32 * sizeof(uint32_t) + 128;
 }
 
 template <int STORE>
-__global__ void __launch_bounds__(kThreads) fanout_kernel(const FanoutParams p) {
+__global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
   cpbus_event* s_batch = reinterpret_cast<cpbus_event*>(smem);
   uint64_t* s_rhash = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 32);
   uint2* s_meta = reinterpret_cast<uint2*>(smem + (size_t)cap * 40);
-  uint64_t* s_pow = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 48);
-  BatchSummary* s_sum = reinterpret_cast<BatchSummary*>(smem + (size_t)cap * 56 + 65 * 8);
+  uint64_t* s_q = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 48);
+  uint64_t* s_pow = s_q + cap + 2;                                   // 16-byte aligned (TMA destination)
+  BatchSummary* s_sum = reinterpret_cast<BatchSummary*>(s_pow + cap + 66);
   uint32_t* s_tick = reinterpret_cast<uint32_t*>(s_sum + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = p.n_ev;
 
   // ---- stage the batch: one elected thread drives the TMA engine ----
-  if (tid == 0) {
-    s_sum->present = 0; s_sum->has_unicast = 0; s_sum->hfull = 0;
-    mbar_init(&s_sum->mbar, 1);
-  }
+  if (tid == 0) mbar_init(&s_sum->mbar, 1);
   __syncthreads();
-  if (n) {
-    if (tid == 0) {
-      mbar_expect_tx(&s_sum->mbar, n * 32u);
-      bulk_g2s(s_batch, p.batch, n * 32u, &s_sum->mbar);
-    }
-    // powers of P do not depend on the batch: compute them while the copy is in flight
-    for (uint32_t i = tid; i < cap + 65; i += kThreads) s_pow[i] = pow_p(i);
-    mbar_wait(&s_sum->mbar, 0);
-  } else {
-    for (uint32_t i = tid; i < cap + 65; i += kThreads) s_pow[i] = pow_p(i);
+  if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
+    const uint32_t pow_bytes = ((cap + 65u) * 8u + 15u) & ~15u;
+    mbar_expect_tx(&s_sum->mbar, n * 32u + pow_bytes);
+    if (n) bulk_g2s(s_batch, p.batch, n * 32u, &s_sum->mbar);
+    bulk_g2s(s_pow, p.pow_table, pow_bytes, &s_sum->mbar);
   }
 
-  // ---- per-batch precompute, once per CTA ----
-  {
-    uint32_t present = 0, uni = 0;
-    for (uint32_t i = tid; i < n; i += kThreads) {
-      const ulonglong4 w = *reinterpret_cast<const ulonglong4*>(&s_batch[i]);
-      s_rhash[i] = record_hash_words(w.x, w.y, w.z, w.w);
-      const uint32_t code = (uint32_t)w.z, target = (uint32_t)w.w;
-      uint32_t codebit = 0;
-      if (target == CPBUS_TARGET_ALL) { codebit = code < 32 ? (1u << code) : 0u; present |= codebit; }
-      else uni = 1;
-      s_meta[i] = make_uint2(codebit, target);
+  // software pipeline, stage 0: the first subscriber's control block (and timer slot) is requested
+  // before anything else so that its DRAM round trip overlaps the staging below
+  const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
+  const uint32_t tk_slot = lane / J, tk_j = lane % J;
+  const bool timers_on = p.timers_on && K;
+  const uint32_t wstride = gridDim.x * kWarpsPerCta;
+  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca, tb = ca;
+  if (s < p.n_subs) {
+    const uint4* c = reinterpret_cast<const uint4*>(p.ctl + s);
+    ca = c[0]; cb = c[1];
+    if (timers_on && tk_slot < K) {
+      const uint4* t = reinterpret_cast<const uint4*>(p.timers + (size_t)s * K + tk_slot);
+      ta = t[0]; tb = t[1];
     }
-    present = __reduce_or_sync(0xffffffffu, present);
-    uni = __reduce_or_sync(0xffffffffu, uni);
-    if (lane == 0) { if (present) atomicOr(&s_sum->present, present); if (uni) atomicOr(&s_sum->has_unicast, 1u); }
   }
-  __syncthreads();
-  if (p.use_digest) {   // H(batch as a dense run) = sum r_i * P^(n-1-i)
-    uint64_t part = 0;
-    for (uint32_t i = tid; i < n; i += kThreads) part += s_rhash[i] * s_pow[n - 1 - i];
-    part = warp_sum64(part);
-    if (lane == 0) s_sum->red[warp] = part;
+
+  // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
+  // descriptor = [rhash | meta | Q] (24*cap + 16 bytes, same layout as shared memory) + {present, has_unicast, hist[32]}
+  const uint32_t desc_words16 = (24u * cap + 16u) / 16u;
+  uint4* s_desc = reinterpret_cast<uint4*>(s_rhash);
+  uint4* g_desc = reinterpret_cast<uint4*>(p.desc);
+  uint32_t* g_sum = reinterpret_cast<uint32_t*>(p.desc + (size_t)desc_words16 * 16u);
+  if (blockIdx.x == 0) {
+    if (tid == 0) { s_sum->present = 0; s_sum->has_unicast = 0; }
+    if (tid < 32) s_sum->hist[tid] = 0;
+    mbar_wait(&s_sum->mbar, 0);
     __syncthreads();
-    if (tid == 0) { uint64_t t = 0; for (int w = 0; w < kWarpsPerCta; w++) t += s_sum->red[w]; s_sum->hfull = t; }
+    {
+      uint32_t present = 0, uni = 0;
+      for (uint32_t i = tid; i < n; i += kThreads) {
+        const ulonglong4 w = *reinterpret_cast<const ulonglong4*>(&s_batch[i]);
+        s_rhash[i] = record_hash_words(w.x, w.y, w.z, w.w);
+        const uint32_t code = (uint32_t)w.z, target = (uint32_t)w.w;
+        uint32_t codebit = 0;
+        if (target == CPBUS_TARGET_ALL) {
+          if (code < 32) { codebit = 1u << code; atomicAdd(&s_sum->hist[code], 1u); }
+          present |= codebit;
+        } else uni = 1;
+        s_meta[i] = make_uint2(codebit, target);
+      }
+      present = __reduce_or_sync(0xffffffffu, present);
+      uni = __reduce_or_sync(0xffffffffu, uni);
+      if (lane == 0) { if (present) atomicOr(&s_sum->present, present); if (uni) atomicOr(&s_sum->has_unicast, 1u); }
+    }
+    __syncthreads();
+    {   // Q: exclusive prefix sums of w_i = H(e_i) P^(n-1-i); Q[n] is the whole batch as one dense run
+      const uint32_t E = (n + kThreads - 1) / kThreads;
+      const uint32_t lo = min(n, (uint32_t)tid * E), hi = min(n, lo + E);
+      uint64_t sum = 0;
+      for (uint32_t i = lo; i < hi; i++) sum += s_rhash[i] * s_pow[n - 1 - i];
+      uint64_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t l = __shfl_up_sync(0xffffffffu, (uint32_t)incl, o), h = __shfl_up_sync(0xffffffffu, (uint32_t)(incl >> 32), o);
+        if (lane >= o) incl += ((uint64_t)h << 32) | l;
+      }
+      if (lane == 31) s_sum->red[warp] = incl;
+      __syncthreads();
+      uint64_t run = incl - sum;
+      for (int w = 0; w < warp; w++) run += s_sum->red[w];
+      for (uint32_t i = lo; i < hi; i++) { s_q[i] = run; run += s_rhash[i] * s_pow[n - 1 - i]; }
+      if (tid == 0) { uint64_t t = 0; for (int w = 0; w < kWarpsPerCta; w++) t += s_sum->red[w]; s_q[n] = t; }
+      __syncthreads();
+    }
+    for (uint32_t i = tid; i < desc_words16; i += kThreads) g_desc[i] = s_desc[i];
+    if (tid < 32) g_sum[2 + tid] = s_sum->hist[tid];
+    if (tid == 0) { g_sum[0] = s_sum->present; g_sum[1] = s_sum->has_unicast; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
+  } else {
+    if (tid == 0) {
+      unsigned long long seen;
+      do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.desc_ready) : "memory"); } while (seen < p.launch_seq);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < desc_words16; i += kThreads) s_desc[i] = __ldcg(g_desc + i);
+    if (tid < 32) s_sum->hist[tid] = __ldcg(g_sum + 2 + tid);
+    if (tid == 0) { s_sum->present = __ldcg(g_sum); s_sum->has_unicast = __ldcg(g_sum + 1); }
+    mbar_wait(&s_sum->mbar, 0);
     __syncthreads();
   }
   const uint32_t present = s_sum->present;
   const bool has_unicast = s_sum->has_unicast != 0;
-  const uint64_t hfull = s_sum->hfull;
   const uint32_t Rm = p.ring_cap - 1;
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
   uint32_t* my_tick = s_tick + warp * 32;
-
   unsigned long long acc_deliv = 0, acc_ticks = 0, acc_over = 0;
   bool bulk_pending = false;
 
-  const uint32_t wstride = gridDim.x * kWarpsPerCta;
-  for (uint32_t s = blockIdx.x * kWarpsPerCta + warp; s < p.n_subs; s += wstride) {
-    const uint32_t m = p.mask[s];
+  // software pipeline: the control block (and timer slot) of the NEXT subscriber is in flight
+  // while the current one is being written, so no DRAM round trip is exposed per subscriber
+  for (; s < p.n_subs; s += wstride) {
+    const uint4 cur_a = ca, cur_b = cb, cur_ta = ta, cur_tb = tb;
+    {
+      const uint32_t sn = s + wstride;
+      if (sn < p.n_subs) {
+        const uint4* c = reinterpret_cast<const uint4*>(p.ctl + sn);
+        ca = c[0]; cb = c[1];
+        if (timers_on && tk_slot < K) {
+          const uint4* t = reinterpret_cast<const uint4*>(p.timers + (size_t)sn * K + tk_slot);
+          ta = t[0]; tb = t[1];
+        }
+      }
+    }
+    const uint32_t m = cur_b.z;
     if (!(m & kActiveBit)) continue;
-    const uint64_t tail = p.tail[s];
+    const uint64_t tail = ((uint64_t)cur_a.y << 32) | cur_a.x;
+    const uint64_t head = ((uint64_t)cur_a.w << 32) | cur_a.z;
+    const uint64_t dig = ((uint64_t)cur_b.y << 32) | cur_b.x;
     cpbus_event* ring = p.ring + (size_t)s * p.ring_cap;
     const uint32_t gid = p.sub_base + s;
-    const uint32_t nslots = p.timers_on ? min((m >> kTimerHintShift) & 0xFu, p.K) : 0u;
+    const uint32_t nslots = timers_on ? min((m >> kTimerHintShift) & 0xFu, K) : 0u;
     // dense <=> this mailbox takes every record of the batch (the reference's only mode)
     const bool dense = !has_unicast && ((m & present) == present);
 
     // ---- timers: which ticks fire in (previous watermark, w_now] ----
-    uint32_t n_ticks = 0;
-    bool tk_valid = false; uint64_t tk_due = 0; uint32_t tk_slot = 0, tk_j = 0, tk_src = 0, tk_fired = 0, tk_rank = 0;
-    uint32_t tk_mask = 0;
+    uint32_t n_ticks = 0, tk_mask = 0, tk_rank = 0, tk_src = 0, tk_fired = 0, tk_flags = 0;
+    bool tk_valid = false; uint64_t tk_due = 0, tk_period = 0, tk_due0 = 0;
     if (nslots) {
-      const uint32_t J = 32u / p.K;            // candidate firings per slot handled per launch (host bounds the window)
-      tk_slot = lane / J; tk_j = lane % J;
-      uint64_t due0 = 0, period = 0; uint32_t fl = 0;
       if (tk_slot < nslots) {
-        const DevTimer t = p.timers[(size_t)s * p.K + tk_slot];
-        due0 = t.next_due; period = t.period; fl = t.flags; tk_src = t.source_id; tk_fired = t.fired;
+        tk_due0 = ((uint64_t)cur_ta.y << 32) | cur_ta.x; tk_period = ((uint64_t)cur_ta.w << 32) | cur_ta.z;
+        tk_src = cur_tb.x; tk_fired = cur_tb.y; tk_flags = cur_tb.z;
       }
-      tk_due = due0 + (uint64_t)tk_j * period;
-      tk_valid = (fl & kTimerActive) && tk_due <= p.w_now && (tk_j == 0 || !(fl & kTimerOneshot));
+      tk_due = tk_due0 + (uint64_t)tk_j * tk_period;
+      tk_valid = (tk_flags & kTimerActive) && tk_due <= p.w_now && (tk_j == 0 || !(tk_flags & kTimerOneshot));
       tk_mask = __ballot_sync(0xffffffffu, tk_valid);
       n_ticks = __popc(tk_mask);
       if (n_ticks) {
@@ -261,6 +342,18 @@ __global__ void __launch_bounds__(kThreads) fanout_kernel(const FanoutParams p) 
         }
       }
     }
+    uint32_t tk_pos = 0;   // events with ts < due stay in front of the tick (lower_bound over the sorted batch)
+    if (tk_valid) {
+      uint32_t lo = 0, hi = n;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_batch[mid].ts_ns < tk_due) lo = mid + 1; else hi = mid;
+      }
+      tk_pos = lo;
+    }
+
+    uint32_t k = 0;           // records appended to this mailbox by this launch
+    uint64_t dsum = 0;        // sum of H(record) * P^(k-1-out) over them
 
     if (dense && n_ticks == 0) {
       // ================= dense run: copy the staged batch into the ring =================
@@ -284,26 +377,61 @@ __global__ void __launch_bounds__(kThreads) fanout_kernel(const FanoutParams p) 
           st_v4(reinterpret_cast<unsigned char*>(ring + (((uint32_t)tail + (q >> 1)) & Rm)) + (q & 1u) * 16u, v);
         }
       }
-      if (lane == 0) {
-        const uint64_t nt = tail + n;
-        p.tail[s] = nt;
-        if (p.use_digest) p.digest[s] = p.digest[s] * s_pow[n] + hfull;
-        if (!p.lossless && nt > p.ring_cap) {
-          const uint64_t h = p.head[s], floor_h = nt - p.ring_cap;
-          if (h < floor_h) { p.head[s] = floor_h; acc_over += floor_h - h; }
-        }
-        acc_deliv += n;
+      k = n;
+      if (p.use_digest) dsum = s_q[n];
+    } else if (dense) {
+      // ================= dense run with interleaved ticks: O(#ticks) bookkeeping =================
+      if (tk_valid) my_tick[tk_rank] = tk_pos;
+      __syncwarp();
+      k = n + n_ticks;
+      for (uint32_t i = lane; i < n; i += 32) {
+        uint32_t out = i;
+        for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= i) ? 1u : 0u;
+        const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+        st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
       }
-      continue;
-    }
-
-    // ================= general run: filter and/or interleaved ticks =================
-    const uint32_t nchunks = (n + 31) >> 5;
-    // pass A: match bitmap, 32 events per ballot; lane c keeps the word of chunk c
-    uint32_t myword = 0;
-    if (dense) {
-      if ((uint32_t)lane < nchunks) myword = ((uint32_t)lane == nchunks - 1 && (n & 31u)) ? ((1u << (n & 31u)) - 1u) : 0xffffffffu;
+      if (tk_valid) {
+        const uint32_t out = tk_pos + tk_rank;
+        const uint64_t w0 = (uint64_t)tk_fired + tk_j, w1 = tk_due;
+        const uint64_t w2 = (uint64_t)CPBUS_TIMER_EXPIRED | ((uint64_t)tk_src << 32);
+        const uint64_t w3 = (uint64_t)gid | ((uint64_t)CPBUS_F_TICK << 32);
+        const uint4 a = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+        const uint4 b = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
+        st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+        if (p.use_digest) {
+          // the run of events in front of this tick keeps its internal weights and is shifted by the
+          // ticks still to come: (Q[pos_r] - Q[pos_{r-1}]) * P^(n_ticks - r)
+          const uint32_t prev = tk_rank ? my_tick[tk_rank - 1] : 0u;
+          dsum = (s_q[tk_pos] - s_q[prev]) * s_pow[n_ticks - tk_rank] + record_hash_words(w0, w1, w2, w3) * s_pow[k - 1 - out];
+          if (tk_rank == n_ticks - 1) dsum += s_q[n] - s_q[tk_pos];
+        }
+      }
+      if (p.use_digest) dsum = warp_sum64(dsum);
+      __syncwarp();
+    } else if (!has_unicast && n_ticks == 0) {
+      // ================= filtered run, single pass: ballot + running rank =================
+      uint32_t kk = ((m >> lane) & 1u) ? s_sum->hist[lane] : 0u;
+      kk = __reduce_add_sync(0xffffffffu, kk);
+      k = kk;
+      uint32_t base = 0;
+      const uint32_t nchunks = (n + 31) >> 5;
+      for (uint32_t c = 0; c < nchunks; c++) {
+        const uint32_t i = c * 32 + lane;
+        const bool match = i < n && (m & s_meta[i].x) != 0;
+        const uint32_t w = __ballot_sync(0xffffffffu, match);
+        if (match) {
+          const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
+          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+          if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+        }
+        base += __popc(w);
+      }
+      if (p.use_digest) dsum = warp_sum64(dsum);
     } else {
+      // ================= general run: filter + unicast + interleaved ticks, two passes =================
+      const uint32_t nchunks = (n + 31) >> 5;
+      uint32_t myword = 0;   // pass A: match bitmap, lane c keeps the ballot of chunk c
       for (uint32_t c = 0; c < nchunks; c++) {
         const uint32_t i = c * 32 + lane;
         bool match = false;
@@ -314,85 +442,70 @@ __global__ void __launch_bounds__(kThreads) fanout_kernel(const FanoutParams p) 
         const uint32_t w = __ballot_sync(0xffffffffu, match);
         if ((uint32_t)lane == c) myword = w;
       }
-    }
-    // exclusive prefix of popcounts over chunks: wprefix(lane c) = matches before chunk c
-    uint32_t wcount = __popc(myword), wprefix = wcount;
+      uint32_t wcount = __popc(myword), wprefix = wcount;   // exclusive prefix of popcounts over chunks
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, wprefix, o);
-      if (lane >= o) wprefix += t;
-    }
-    const uint32_t k_ev = __shfl_sync(0xffffffffu, wprefix, 31);
-    wprefix -= wcount;
-
-    // ticks: position among the matched events, then output slot
-    uint32_t tk_mp = 0;
-    if (n_ticks) {
-      uint32_t pos = 0;
-      if (tk_valid) {                         // lower_bound: events with ts < due stay in front of the tick
-        uint32_t lo = 0, hi = n;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (s_batch[mid].ts_ns < tk_due) lo = mid + 1; else hi = mid;
-        }
-        pos = lo;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wprefix, o);
+        if (lane >= o) wprefix += t;
       }
-      const uint32_t pc = pos >> 5;           // chunk of the first event behind the tick
-      const uint32_t wsel = __shfl_sync(0xffffffffu, myword, pc & 31);
-      const uint32_t psel = __shfl_sync(0xffffffffu, wprefix, pc & 31);
-      tk_mp = (pos >= n) ? k_ev : psel + __popc(wsel & ((1u << (pos & 31u)) - 1u));
-      if (tk_valid) my_tick[tk_rank] = tk_mp;
+      const uint32_t k_ev = __shfl_sync(0xffffffffu, wprefix, 31);
+      wprefix -= wcount;
+      uint32_t tk_mp = 0;    // matched events in front of each tick
+      if (n_ticks) {
+        const uint32_t pc = tk_pos >> 5;
+        const uint32_t wsel = __shfl_sync(0xffffffffu, myword, pc & 31);
+        const uint32_t psel = __shfl_sync(0xffffffffu, wprefix, pc & 31);
+        tk_mp = (tk_pos >= n) ? k_ev : psel + __popc(wsel & ((1u << (tk_pos & 31u)) - 1u));
+        if (tk_valid) my_tick[tk_rank] = tk_mp;
+        __syncwarp();
+      }
+      k = k_ev + n_ticks;
+      for (uint32_t c = 0; c < nchunks; c++) {   // pass B
+        const uint32_t w = __shfl_sync(0xffffffffu, myword, c);
+        const uint32_t wp = __shfl_sync(0xffffffffu, wprefix, c);
+        if ((w >> lane) & 1u) {
+          const uint32_t i = c * 32 + lane;
+          const uint32_t mrank = wp + __popc(w & ((1u << lane) - 1u));
+          uint32_t out = mrank;
+          for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= mrank) ? 1u : 0u;
+          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+          if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+        }
+      }
+      if (tk_valid) {   // the tick records themselves: {TimerExpired, name} (events/timer.go:31,60)
+        const uint32_t out = tk_mp + tk_rank;
+        const uint64_t w0 = (uint64_t)tk_fired + tk_j, w1 = tk_due;
+        const uint64_t w2 = (uint64_t)CPBUS_TIMER_EXPIRED | ((uint64_t)tk_src << 32);
+        const uint64_t w3 = (uint64_t)gid | ((uint64_t)CPBUS_F_TICK << 32);
+        const uint4 a = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+        const uint4 b = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
+        st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+        if (p.use_digest) dsum += record_hash_words(w0, w1, w2, w3) * s_pow[k - 1 - out];
+      }
+      if (p.use_digest) dsum = warp_sum64(dsum);
       __syncwarp();
     }
-    const uint32_t k = k_ev + n_ticks;
 
-    uint64_t dacc = 0;
-    // pass B: every matched event goes to output index (matched rank + ticks in front of it)
-    for (uint32_t c = 0; c < nchunks; c++) {
-      const uint32_t w = __shfl_sync(0xffffffffu, myword, c);
-      const uint32_t wp = __shfl_sync(0xffffffffu, wprefix, c);
-      if ((w >> lane) & 1u) {
-        const uint32_t i = c * 32 + lane;
-        const uint32_t mrank = wp + __popc(w & ((1u << lane) - 1u));
-        uint32_t out = mrank;
-        for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= mrank) ? 1u : 0u;
-        const uint4 a = s4[2 * i], b = s4[2 * i + 1];
-        st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-        if (p.use_digest) dacc += s_rhash[i] * s_pow[k - 1 - out];
-      }
-    }
-    if (tk_valid) {   // the tick records themselves: {TimerExpired, name} (events/timer.go:31,60)
-      const uint32_t out = tk_mp + tk_rank;
-      const uint64_t w0 = (uint64_t)tk_fired + tk_j, w1 = tk_due;
-      const uint64_t w2 = (uint64_t)CPBUS_TIMER_EXPIRED | ((uint64_t)tk_src << 32);
-      const uint64_t w3 = (uint64_t)gid | ((uint64_t)CPBUS_F_TICK << 32);
-      const uint4 a = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
-      const uint4 b = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
-      st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-      if (p.use_digest) dacc += record_hash_words(w0, w1, w2, w3) * s_pow[k - 1 - out];
-    }
-    if (n_ticks) {   // re-arm: one lane per slot writes its timer back
-      const uint32_t J = 32u / p.K;
+    if (n_ticks) {   // re-arm: one lane per slot writes its timer back (events/timer.go: ticker keeps running)
       const uint32_t slotmask = (J == 32 ? 0xffffffffu : ((1u << J) - 1u)) << (tk_slot * J);
       const uint32_t fired_here = __popc(tk_mask & slotmask);
       if (tk_j == 0 && tk_slot < nslots && fired_here) {
-        DevTimer* t = &p.timers[(size_t)s * p.K + tk_slot];
-        const uint32_t fl = t->flags;
-        if (fl & kTimerOneshot) t->flags = fl & ~kTimerActive;
-        else t->next_due = t->next_due + (uint64_t)fired_here * t->period;
-        t->fired = tk_fired + fired_here;
+        DevTimer* t = &p.timers[(size_t)s * K + tk_slot];
+        uint4 na = cur_ta, nb = cur_tb;
+        if (tk_flags & kTimerOneshot) nb.z = tk_flags & ~kTimerActive;
+        else { const uint64_t nd = tk_due0 + (uint64_t)fired_here * tk_period; na.x = (uint32_t)nd; na.y = (uint32_t)(nd >> 32); }
+        nb.y = tk_fired + fired_here;
+        st_v8(t, na, nb);
       }
-      __syncwarp();
     }
-    if (p.use_digest) dacc = warp_sum64(dacc);
-    if (lane == 0 && k) {
+    if (lane == 0 && k) {   // one full-sector write of the control block
       const uint64_t nt = tail + k;
-      p.tail[s] = nt;
-      if (p.use_digest) p.digest[s] = p.digest[s] * s_pow[k] + dacc;
-      if (!p.lossless && nt > p.ring_cap) {
-        const uint64_t h = p.head[s], floor_h = nt - p.ring_cap;
-        if (h < floor_h) { p.head[s] = floor_h; acc_over += floor_h - h; }
-      }
+      uint64_t nh = head;
+      if (!p.lossless && nt > p.ring_cap && nh < nt - p.ring_cap) { acc_over += nt - p.ring_cap - nh; nh = nt - p.ring_cap; }
+      const uint64_t nd = p.use_digest ? dig * s_pow[k] + dsum : dig;
+      st_v8(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), (uint32_t)nh, (uint32_t)(nh >> 32)),
+            make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u));
       acc_deliv += k; acc_ticks += n_ticks;
     }
   }
@@ -400,19 +513,19 @@ __global__ void __launch_bounds__(kThreads) fanout_kernel(const FanoutParams p) 
   if (STORE == CPBUS_STORE_BULK && bulk_pending && lane == 0)
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged batch must outlive the TMA reads
   if (lane == 0) {
-    if (acc_deliv) atomicAdd(&p.stats->deliveries, acc_deliv);
-    if (acc_ticks) atomicAdd(&p.stats->ticks, acc_ticks);
-    if (acc_over) atomicAdd(&p.stats->overwritten, acc_over);
+    DevStatSlot* st = &p.stats->slot[(blockIdx.x * kWarpsPerCta + warp) % kStatSlots];
+    if (acc_deliv) atomicAdd(&st->deliveries, acc_deliv);
+    if (acc_ticks) atomicAdd(&st->ticks, acc_ticks);
+    if (acc_over) atomicAdd(&st->overwritten, acc_over);
   }
 }
 
 // Lossless mode (reference semantics, events/subscriber.go:30-32: a full channel
 // blocks the sender): before a batch is fanned out, count for every mailbox what
 // the batch would append and flag any that lacks the room.  Thread per subscriber.
-__global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w_now, const uint32_t* mask,
-                             const unsigned long long* tail, const unsigned long long* head, const DevTimer* timers,
-                             uint32_t n_subs, uint32_t ring_cap, uint32_t K, uint32_t sub_base, uint32_t timers_on,
-                             DevStats* stats) {
+__global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w_now, const SubCtl* ctl,
+                             const DevTimer* timers, uint32_t n_subs, uint32_t ring_cap, uint32_t K, uint32_t sub_base,
+                             uint32_t timers_on, DevStats* stats) {
   __shared__ uint32_t hist[32];
   __shared__ uint32_t s_uni;
   if (threadIdx.x < 32) hist[threadIdx.x] = 0;
@@ -426,7 +539,8 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
   __syncthreads();
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_subs) return;
-  const uint32_t m = mask[s];
+  const SubCtl c = ctl[s];
+  const uint32_t m = c.mask;
   if (!(m & kActiveBit)) return;
   uint64_t k = 0;
   for (uint32_t c = 0; c < CPBUS_N_CODES; c++) if ((m >> c) & 1u) k += hist[c];
@@ -440,15 +554,15 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
     if ((tm.flags & kTimerActive) && tm.next_due <= w_now)
       k += (tm.flags & kTimerOneshot) ? 1u : (w_now - tm.next_due) / tm.period + 1u;
   }
-  if (tail[s] - head[s] + k > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
+  if (c.tail - c.head + k > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
 }
 
 // (count, digest) folds over a range of mailboxes: one 32-byte result instead of 16 B per subscriber
-__global__ void digest_fold_kernel(const unsigned long long* tail, const unsigned long long* digest, uint32_t first,
-                                   uint32_t n, uint32_t sub_base, unsigned long long* out4) {
+__global__ void digest_fold_kernel(const SubCtl* ctl, uint32_t first, uint32_t n, uint32_t sub_base,
+                                   unsigned long long* out4) {
   unsigned long long c = 0, d = 0, x = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long t = tail[first + i], g = digest[first + i];
+    const unsigned long long t = ctl[first + i].tail, g = ctl[first + i].digest;
     c += t; d += g;
     x ^= record_hash_words(g, t, sub_base + first + i, 0);
   }

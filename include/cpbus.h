@@ -178,8 +178,12 @@ int cpbus_digest_fold(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t out
  * events, oldest first, stopping at a NonEvent.  Host-side, no 100 ms sleep. */
 int cpbus_debug_events(cpbus_t* bus, cpbus_event* out, size_t cap, size_t* n);
 int cpbus_stats(cpbus_t* bus, cpbus_stats_t* out);
-/* device pointers for zero-copy inspection by tests/bench (ring, tail) */
-int cpbus_device_ptrs(cpbus_t* bus, void** ring, void** tail, void** mask, void** digest);
+/* HBM layout, for zero-copy inspection by tests/bench: `ring` = n_max_subs mailboxes of
+ * ring_cap records each (mailbox s starts at ring + s*ring_cap*32 bytes; slot of the j-th
+ * delivered record = j mod ring_cap); `ctl` = n_max_subs control blocks of 32 bytes:
+ * {u64 tail (records ever delivered); u64 head (consumer cursor); u64 digest; u32 mask
+ * (bit 31 = subscribed, bits 24..27 = timer slots in use); u32 pad}. */
+int cpbus_device_ptrs(cpbus_t* bus, void** ring, void** ctl);
 
 /* ---- names: EventCode.String (events/eventcode_string.go:9-15), FromString (events/events.go:52-86) ---- */
 const char* cpbus_code_name(int code);               /* NULL if out of range      */
