@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcpbus.so")
+LIB_PATH = os.environ.get("CPBUS_LIB") or os.path.join(HERE, "libcpbus.so")   # CPBUS_LIB: A/B builds of the same library
 
 N_CODES = 17
 MASK_ALL = 0x0001FFFF

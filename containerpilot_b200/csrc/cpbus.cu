@@ -56,6 +56,7 @@ struct cpbus {
   unsigned long long* d_desc_ready = nullptr;
   unsigned long long launch_seq = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
+  uint32_t hints = 1;                     // bit0: control blocks / timer slots evict_last in L2 (+3 % at 65,536 subscribers)
   unsigned long long* d_fold = nullptr;   // 4 words
   cpbus_event* d_batch[2] = {nullptr, nullptr};
   cpbus_event* h_batch[2] = {nullptr, nullptr};   // pinned staging
@@ -125,8 +126,9 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     // Several waves of short-lived CTAs rather than one persistent wave: the hardware CTA scheduler
     // balances the two dies / SM speed spread for free (pure-store microbenchmark, scripts/write_ceiling.cu:
     // 6.0 TB/s with one resident wave, 6.9 TB/s with >= 32 CTAs per SM).  Per-CTA setup here is a descriptor
-    // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is ~14 CTAs per SM
-    // (65,536 subscribers: 4 per warp -> 88.5 % of peak vs 83.3 % persistent, 75.7 % at 1 per warp).
+    // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is 4-8 mailboxes per warp
+    // (65,536 subscribers: 4 per warp -> 90.9 % of peak vs 83.3 % persistent, 75.7 % at 1 per warp;
+    //  1,048,576 subscribers with timers: 8 per warp -> 87.0 % vs 83.1 % at 64 per warp).
     if (occ_smem != smem) {
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE>, kThreads, smem));
       occ_smem = smem;
@@ -134,7 +136,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     }
     const uint32_t need = (p.n_subs + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t spw = b->subs_per_warp;
-    if (!spw) spw = std::max(1u, need / (uint32_t)(b->sm_count * 14));
+    if (!spw) spw = std::max(1u, std::min(8u, need / (uint32_t)(b->sm_count * 14)));
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
     (void)occ_blocks;
   }
@@ -152,6 +154,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
+  p.hints = b->hints;
   const size_t smem = fanout_smem_bytes(p.smem_cap);
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
@@ -302,6 +305,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  if (const char* e = getenv("CPBUS_HINTS")) b->hints = (uint32_t)atoi(e);
   if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
   int rc = CPBUS_OK;
   auto fail = [&](int code) { cpbus_destroy(b); return code; };

@@ -73,6 +73,7 @@ struct FanoutParams {
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
   uint32_t smem_cap;          // n_ev rounded up to 32 (shared-memory carve-up)
+  uint32_t hints;             // bit0: keep control blocks / timer slots in L2 (evict_last)
 };
 
 // ---------------------------------------------------------------- helpers ---
@@ -122,6 +123,25 @@ template <int STORE>
 __device__ __forceinline__ void st_record(cpbus_event* dst, const uint4& a, const uint4& b) {
   if (STORE == CPBUS_STORE_V8) st_v8(dst, a, b);
   else { st_v4(dst, a); st_v4(reinterpret_cast<unsigned char*>(dst) + 16, b); }
+}
+// 32-byte sector load/store with an L2 eviction-priority hint (control blocks and timer slots are
+// re-read every launch; ring records are write-once streams)
+__device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, uint64_t pol, bool hinted) {
+  if (hinted)
+    asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(src), "l"(pol));
+  else
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(src));
+}
+__device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4& b, uint64_t pol, bool hinted) {
+  if (hinted)
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
+                 "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol)
+                 : "memory");
+  else st_v8(dst, a, b);
 }
 // TMA 1-D bulk copies (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
@@ -208,13 +228,12 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca, tb = ca;
+  const bool keep = p.hints & 1u;
+  uint64_t pol_keep = 0;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   if (s < p.n_subs) {
-    const uint4* c = reinterpret_cast<const uint4*>(p.ctl + s);
-    ca = c[0]; cb = c[1];
-    if (timers_on && tk_slot < K) {
-      const uint4* t = reinterpret_cast<const uint4*>(p.timers + (size_t)s * K + tk_slot);
-      ta = t[0]; tb = t[1];
-    }
+    ld_sector(p.ctl + s, ca, cb, pol_keep, keep);
+    if (timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, ta, tb, pol_keep, keep);
   }
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
@@ -298,12 +317,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
     {
       const uint32_t sn = s + wstride;
       if (sn < p.n_subs) {
-        const uint4* c = reinterpret_cast<const uint4*>(p.ctl + sn);
-        ca = c[0]; cb = c[1];
-        if (timers_on && tk_slot < K) {
-          const uint4* t = reinterpret_cast<const uint4*>(p.timers + (size_t)sn * K + tk_slot);
-          ta = t[0]; tb = t[1];
-        }
+        ld_sector(p.ctl + sn, ca, cb, pol_keep, keep);
+        if (timers_on && tk_slot < K) ld_sector(p.timers + (size_t)sn * K + tk_slot, ta, tb, pol_keep, keep);
       }
     }
     const uint32_t m = cur_b.z;
@@ -496,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
         if (tk_flags & kTimerOneshot) nb.z = tk_flags & ~kTimerActive;
         else { const uint64_t nd = tk_due0 + (uint64_t)fired_here * tk_period; na.x = (uint32_t)nd; na.y = (uint32_t)(nd >> 32); }
         nb.y = tk_fired + fired_here;
-        st_v8(t, na, nb);
+        st_sector(t, na, nb, pol_keep, keep);
       }
     }
     if (lane == 0 && k) {   // one full-sector write of the control block
@@ -504,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
       uint64_t nh = head;
       if (!p.lossless && nt > p.ring_cap && nh < nt - p.ring_cap) { acc_over += nt - p.ring_cap - nh; nh = nt - p.ring_cap; }
       const uint64_t nd = p.use_digest ? dig * s_pow[k] + dsum : dig;
-      st_v8(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), (uint32_t)nh, (uint32_t)(nh >> 32)),
-            make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u));
+      st_sector(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), (uint32_t)nh, (uint32_t)(nh >> 32)),
+                make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u), pol_keep, keep);
       acc_deliv += k; acc_ticks += n_ticks;
     }
   }
