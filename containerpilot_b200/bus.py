@@ -144,6 +144,16 @@ class Bus:
         nat.check(self._lib.cpbus_digest_fold(self._h, first_sub, n, C.byref(out)), "cpbus_digest_fold")
         return tuple(out)
 
+    def digest_fold_begin(self, first_sub: int, n: int) -> int:
+        t = C.c_uint32()
+        nat.check(self._lib.cpbus_digest_fold_begin(self._h, first_sub, n, C.byref(t)), "cpbus_digest_fold_begin")
+        return t.value
+
+    def digest_fold_end(self, ticket: int):
+        out = (C.c_uint64 * 4)()
+        nat.check(self._lib.cpbus_digest_fold_end(self._h, ticket, C.byref(out)), "cpbus_digest_fold_end")
+        return tuple(out)
+
     def debug_events(self):
         out = np.zeros(10, dtype=EVENT_DTYPE)
         n = C.c_size_t()

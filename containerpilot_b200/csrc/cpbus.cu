@@ -57,7 +57,10 @@ struct cpbus {
   unsigned long long launch_seq = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
   uint32_t hints = 1;                     // bit0: control blocks / timer slots evict_last in L2 (+3 % at 65,536 subscribers)
-  unsigned long long* d_fold = nullptr;   // 4 words
+  static constexpr int kFoldSlots = 8;
+  unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
+  cudaEvent_t fold_done[kFoldSlots] = {};
+  uint32_t fold_next = 0;
   cpbus_event* d_batch[2] = {nullptr, nullptr};
   cpbus_event* h_batch[2] = {nullptr, nullptr};   // pinned staging
   cudaEvent_t h2d_done[2] = {nullptr, nullptr};
@@ -329,7 +332,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_ring, N * R * sizeof(cpbus_event));
   ALLOC(b->d_ctl, N * sizeof(SubCtl));
   if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
-  ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32); ALLOC(b->d_pow, kPowTableLen * 8);
+  ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32 * cpbus::kFoldSlots); ALLOC(b->d_pow, kPowTableLen * 8);
   ALLOC(b->d_desc, fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 128);
   if (cudaMemsetAsync(b->d_desc_ready, 0, 128, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   for (int i = 0; i < 2; i++) {
@@ -339,7 +342,9 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   }
 #undef ALLOC
   if (cudaMallocHost((void**)&b->h_stats, sizeof(DevStats)) != cudaSuccess) return fail(CPBUS_ENOMEM);
-  if (cudaMallocHost((void**)&b->h_fold, 32) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  if (cudaMallocHost((void**)&b->h_fold, 32 * cpbus::kFoldSlots) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  for (int i = 0; i < cpbus::kFoldSlots; i++)
+    if (cudaEventCreateWithFlags(&b->fold_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   // rings are NOT cleared: a slot is only ever read after it has been written (head/tail bound every read)
   bool ok = cudaMemsetAsync(b->d_ctl, 0, N * sizeof(SubCtl), b->stream) == cudaSuccess &&
             cudaMemsetAsync(b->d_stats, 0, sizeof(DevStats), b->stream) == cudaSuccess &&
@@ -375,6 +380,7 @@ int cpbus_destroy(cpbus_t* b) {
   }
   if (b->h_stats) cudaFreeHost(b->h_stats);
   if (b->h_fold) cudaFreeHost(b->h_fold);
+  for (int i = 0; i < cpbus::kFoldSlots; i++) if (b->fold_done[i]) cudaEventDestroy(b->fold_done[i]);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
   return CPBUS_OK;
@@ -666,21 +672,37 @@ int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out
   return CPBUS_OK;
 }
 
-int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4]) {
-  if (!b || !out || !n) return CPBUS_EINVAL;
+int cpbus_digest_fold_begin(cpbus_t* b, uint32_t first_sub, uint32_t n, uint32_t* ticket) {
+  if (!b || !ticket || !n) return CPBUS_EINVAL;
   const uint32_t l = first_sub - b->cfg.sub_id_base;
   if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
-  CK(cudaMemsetAsync(b->d_fold, 0, 32, b->stream));
+  const uint32_t slot = b->fold_next++ % cpbus::kFoldSlots;
+  unsigned long long* d = b->d_fold + 4 * slot;
+  CK(cudaMemsetAsync(d, 0, 32, b->stream));
   const uint32_t threads = 256, grid = std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)b->sm_count * 4);
-  digest_fold_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, l, n, b->cfg.sub_id_base, b->d_fold);
+  digest_fold_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, l, n, b->cfg.sub_id_base, d);
   CK(cudaGetLastError());
   b->st.kernel_launches++;
-  CK(cudaMemcpyAsync(b->h_fold, b->d_fold, 32, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
-  for (int i = 0; i < 4; i++) out[i] = b->h_fold[i];
+  CK(cudaMemcpyAsync(b->h_fold + 4 * slot, d, 32, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaEventRecord(b->fold_done[slot], b->stream));
+  *ticket = slot;
   return CPBUS_OK;
+}
+
+int cpbus_digest_fold_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
+  if (!b || !out || ticket >= (uint32_t)cpbus::kFoldSlots) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaEventSynchronize(b->fold_done[ticket]));
+  for (int i = 0; i < 4; i++) out[i] = b->h_fold[4 * ticket + i];
+  return CPBUS_OK;
+}
+
+int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4]) {
+  uint32_t ticket = 0;
+  int rc = cpbus_digest_fold_begin(b, first_sub, n, &ticket);
+  return rc ? rc : cpbus_digest_fold_end(b, ticket, out);
 }
 
 // DebugEvents — events/bus.go:34-54

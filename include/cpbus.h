@@ -172,6 +172,11 @@ int cpbus_digest(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_digest_t* o
 /* XOR-fold / sum of (count, digest) over [first_sub, first_sub+n) computed on the
  * device: one 32-byte D2H instead of 16 B per subscriber. */
 int cpbus_digest_fold(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t out[4]);
+/* Split form: _begin enqueues the fold + the 32-byte D2H on the bus stream and returns a ticket
+ * (up to 8 outstanding); _end waits for that ticket only.  Lets a caller read step i's result
+ * while step i+1 is already running. */
+int cpbus_digest_fold_begin(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint32_t* ticket);
+int cpbus_digest_fold_end(cpbus_t* bus, uint32_t ticket, uint64_t out[4]);
 
 /* ---- observation ---- */
 /* DebugEvents (events/bus.go:34-54): drains the 10-slot ring of the last published

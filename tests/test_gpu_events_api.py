@@ -145,3 +145,14 @@ def test_from_string_and_names():
     assert code == events.None_ and "bogus is not a valid event code" in str(err)      # events.go:85
     assert [events.CodeString(i) for i in range(17)] == G["code_names"]["names"]
     assert events.CodeString(42) == "EventCode(42)"                                    # eventcode_string.go:11
+
+
+def test_cpp_mirror_restates_reference_tests():
+    """The compiled-language host side (containerpilot_b200/csrc/host/events.hpp, C++17 over the C-ABI):
+    events_test.cc restates events/events_test.go + the jobs/control/watches vectors, with real
+    bounded channels and consumer threads."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "containerpilot_b200", "csrc", "host", "events_test")
+    assert os.path.exists(exe), "build with __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("PASS"), r.stdout + r.stderr
