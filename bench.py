@@ -250,6 +250,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing: `value` ----
+    sampler = ClockSampler(local)
+    sampler.start()                                                    # started early so NVML is warm before the timed region
     run_steps(warmup)
     # settle: a fresh box pages in driver/library code lazily; keep warming (untimed) for ~0.3 s of wall clock
     settle, t_settle = 0, time.perf_counter()
@@ -257,8 +259,7 @@ def main():
         run_steps(100); torch.cuda.synchronize(); settle += 100
     barrier()
     st0 = bus.stats()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.samples.clear(); sampler.reasons.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)

@@ -57,7 +57,10 @@ static void TestPubSubInterfaces() {
   ts.Run(ctx, &bus);
   std::vector<Event> expected{Event{Startup, "serviceA"}};
   for (auto& e : expected) tp.Publish(e);
-  std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  for (int spin = 0; spin < 2000; spin++) {
+    { std::lock_guard<std::mutex> l(ts.lock); if (ts.results.size() == expected.size()) break; }
+    std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
   ctx.Cancel();
   auto results = bus.DebugEvents();
   EXPECT(results == expected);
@@ -78,7 +81,10 @@ static void TestPublishSignal() {
   std::vector<std::string> signals{"SIGHUP", "SIGUSR2"};
   std::vector<Event> expected;
   for (auto& s : signals) { expected.push_back(Event{Signal, s}); bus.PublishSignal(s); }
-  std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  for (int spin = 0; spin < 2000; spin++) {
+    { std::lock_guard<std::mutex> l(ts.lock); if (ts.results.size() == expected.size()) break; }
+    std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
   ctx.Cancel();
   auto results = bus.DebugEvents();
   EXPECT(results == expected);
@@ -194,7 +200,12 @@ static void TestConfig1Plumbing() {
   Publisher pub; pub.Register(&bus);
   std::vector<Event> sent;
   for (int i = 0; i < E; i++) { Event e{(EventCode)(1 + i % 16), "src" + std::to_string(i % 64)}; sent.push_back(e); pub.Publish(e); }
-  std::this_thread::sleep_for(std::chrono::milliseconds(200));
+  for (int spin = 0; spin < 10000; spin++) {   // the consumers run concurrently; give them up to 10 s
+    bool all = true;
+    for (auto& s : subs) { std::lock_guard<std::mutex> l(s->lock); all = all && s->results.size() == sent.size(); }
+    if (all) break;
+    std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
   ctx.Cancel();
   for (auto& s : subs) { s->Join(); EXPECT(s->results == sent); }
   pub.Unregister();
