@@ -116,13 +116,13 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
   if (old != -1 && b->dbg_head == b->dbg_tail) b->dbg_tail = (b->dbg_tail + 1) % 10;
 }
 
-template <int STORE>
+template <int STORE, bool TIMERS>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done = false;   // per instantiation
   static size_t occ_smem = ~(size_t)0;
   static int occ_blocks = 1;
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(fanout_kernel<STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   if (!grid) {
@@ -133,7 +133,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     // (65,536 subscribers: 4 per warp -> 90.9 % of peak vs 83.3 % persistent, 75.7 % at 1 per warp;
     //  1,048,576 subscribers with timers: 8 per warp -> 87.0 % vs 83.1 % at 64 per warp).
     if (occ_smem != smem) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE>, kThreads, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE, TIMERS>, kThreads, smem));
       occ_smem = smem;
       if (occ_blocks < 1) occ_blocks = 1;
     }
@@ -143,7 +143,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
     (void)occ_blocks;
   }
-  fanout_kernel<STORE><<<grid, kThreads, smem, b->stream>>>(p);
+  fanout_kernel<STORE, TIMERS><<<grid, kThreads, smem, b->stream>>>(p);
   CK(cudaGetLastError());
   return CPBUS_OK;
 }
@@ -162,10 +162,11 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
+  const bool timers = p.timers_on != 0;
   switch (b->store) {
-    case CPBUS_STORE_V4: rc = launch_fanout_t<CPBUS_STORE_V4>(b, p, grid, smem); break;
-    case CPBUS_STORE_BULK: rc = launch_fanout_t<CPBUS_STORE_BULK>(b, p, grid, smem); break;
-    default: rc = launch_fanout_t<CPBUS_STORE_V8>(b, p, grid, smem); break;
+    case CPBUS_STORE_V4: rc = timers ? launch_fanout_t<CPBUS_STORE_V4, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_V4, false>(b, p, grid, smem); break;
+    case CPBUS_STORE_BULK: rc = timers ? launch_fanout_t<CPBUS_STORE_BULK, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_BULK, false>(b, p, grid, smem); break;
+    default: rc = timers ? launch_fanout_t<CPBUS_STORE_V8, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_V8, false>(b, p, grid, smem); break;
   }
   if (rc) return rc;
   b->st.batches++; b->st.kernel_launches++;

@@ -22,6 +22,12 @@ namespace cpbus_dev {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef CPBUS_TIMERS_MIN_CTAS
+#define CPBUS_TIMERS_MIN_CTAS 3    // timers build: 80 registers, no spills
+#endif
+#ifndef CPBUS_TIMER_PREFETCH
+#define CPBUS_TIMER_PREFETCH 1
+#endif
 #ifndef CPBUS_MIN_CTAS_PER_SM
 #define CPBUS_MIN_CTAS_PER_SM 3   // 80 registers/thread, no spills; 24 resident warps per SM
 #endif
@@ -192,11 +198,14 @@ struct BatchSummary {
 __host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 34 * 4 + 8; }
 
 __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
-  return (size_t)cap * 56 + 16 + (size_t)(cap + 66) * 8 + sizeof(BatchSummary) + kWarpsPerCta * 32 * sizeof(uint32_t) + 128;
+  const size_t scratch = (cap / 2u > 32u ? cap / 2u : 32u) * sizeof(uint32_t);
+  return (size_t)cap * 56 + 16 + (size_t)(cap + 66) * 8 + sizeof(BatchSummary) + kWarpsPerCta * scratch + 128;
 }
 
-template <int STORE>
-__global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel(const FanoutParams p) {
+// TIMERS=false compiles every timer/tick path out (the host knows when no timer is armed): fewer registers,
+// one more resident CTA per SM.
+template <int STORE, bool TIMERS>
+__global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPBUS_MIN_CTAS_PER_SM + 1) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
   cpbus_event* s_batch = reinterpret_cast<cpbus_event*>(smem);
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
   // before anything else so that its DRAM round trip overlaps the staging below
   const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
-  const bool timers_on = p.timers_on && K;
+  const bool timers_on = TIMERS && p.timers_on && K;
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca, tb = ca;
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
   if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   if (s < p.n_subs) {
     ld_sector(p.ctl + s, ca, cb, pol_keep, keep);
-    if (timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, ta, tb, pol_keep, keep);
+    if (CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, ta, tb, pol_keep, keep);
   }
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
@@ -306,19 +315,22 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
   const bool has_unicast = s_sum->has_unicast != 0;
   const uint32_t Rm = p.ring_cap - 1;
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
-  uint32_t* my_tick = s_tick + warp * 32;
+  const uint32_t scratch_words = max(32u, cap / 2u);                   // per warp: 32 tick positions or cap u16 event indices
+  uint32_t* my_tick = s_tick + warp * scratch_words;
   unsigned long long acc_deliv = 0, acc_ticks = 0, acc_over = 0;
   bool bulk_pending = false;
 
   // software pipeline: the control block (and timer slot) of the NEXT subscriber is in flight
   // while the current one is being written, so no DRAM round trip is exposed per subscriber
   for (; s < p.n_subs; s += wstride) {
-    const uint4 cur_a = ca, cur_b = cb, cur_ta = ta, cur_tb = tb;
+    const uint4 cur_a = ca, cur_b = cb;
+    uint4 cur_ta = ta, cur_tb = tb;
+    if (!CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, cur_ta, cur_tb, pol_keep, keep);
     {
       const uint32_t sn = s + wstride;
       if (sn < p.n_subs) {
         ld_sector(p.ctl + sn, ca, cb, pol_keep, keep);
-        if (timers_on && tk_slot < K) ld_sector(p.timers + (size_t)sn * K + tk_slot, ta, tb, pol_keep, keep);
+        if (CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)sn * K + tk_slot, ta, tb, pol_keep, keep);
       }
     }
     const uint32_t m = cur_b.z;
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
     uint32_t n_ticks = 0, tk_mask = 0, tk_rank = 0, tk_src = 0, tk_fired = 0, tk_flags = 0;
     bool tk_valid = false; uint64_t tk_due = 0, tk_period = 0, tk_due0 = 0;
     if (nslots) {
-      if (tk_slot < nslots) {
+      if (TIMERS && tk_slot < nslots) {
         tk_due0 = ((uint64_t)cur_ta.y << 32) | cur_ta.x; tk_period = ((uint64_t)cur_ta.w << 32) | cur_ta.z;
         tk_src = cur_tb.x; tk_fired = cur_tb.y; tk_flags = cur_tb.z;
       }
@@ -424,25 +436,59 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
       if (p.use_digest) dsum = warp_sum64(dsum);
       __syncwarp();
     } else if (!has_unicast && n_ticks == 0) {
-      // ================= filtered run, single pass: ballot + running rank =================
-      uint32_t kk = ((m >> lane) & 1u) ? s_sum->hist[lane] : 0u;
-      kk = __reduce_add_sync(0xffffffffu, kk);
-      k = kk;
-      uint32_t base = 0;
-      const uint32_t nchunks = (n + 31) >> 5;
-      for (uint32_t c = 0; c < nchunks; c++) {
-        const uint32_t i = c * 32 + lane;
-        const bool match = i < n && (m & s_meta[i].x) != 0;
-        const uint32_t w = __ballot_sync(0xffffffffu, match);
-        if (match) {
-          const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
-          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
-          st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-          if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+      if constexpr (!TIMERS) {
+        // ================= filtered run: compact the matching event indices, then an output-centric copy =================
+        // pass 1: ballot 32 events at a time; matching lanes append their event index to the warp's scratch list
+        uint16_t* my_idx = reinterpret_cast<uint16_t*>(my_tick);
+        uint32_t base = 0;
+        const uint32_t nchunks = (n + 31) >> 5;
+        for (uint32_t c = 0; c < nchunks; c++) {
+          const uint32_t i = c * 32 + lane;
+          const bool match = i < n && (m & s_meta[i].x) != 0;
+          const uint32_t w = __ballot_sync(0xffffffffu, match);
+          if (match) my_idx[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)i;
+          base += __popc(w);
         }
-        base += __popc(w);
+        k = base;
+        __syncwarp();
+        // pass 2: lane -> output slot, so stores are fully coalesced and only ceil(k/32) iterations run.
+        // Digest by per-lane Horner in P^32: acc_l = sum_it H(e) (P^32)^(nit_l-1-it); one power lookup per lane at the end.
+        uint64_t acc = 0;
+        const uint64_t p32 = s_pow[32];
+        uint32_t o = lane;
+        for (; o < k; o += 32) {
+          const uint32_t i = my_idx[o];
+          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
+          if (p.use_digest) acc = acc * p32 + s_rhash[i];
+        }
+        if (p.use_digest) {
+          // o is now the first index this lane did NOT write; its last one was o-32 (if any)
+          dsum = (o >= 32 && o - 32 < k) ? acc * s_pow[k - 1 - (o - 32)] : 0ull;
+          dsum = warp_sum64(dsum);
+        }
+        __syncwarp();
+      } else {
+        // timers build: register budget is tighter (80, no spills) — single pass, ballot + running rank
+        uint32_t kk = ((m >> lane) & 1u) ? s_sum->hist[lane] : 0u;
+        kk = __reduce_add_sync(0xffffffffu, kk);
+        k = kk;
+        uint32_t base = 0;
+        const uint32_t nchunks = (n + 31) >> 5;
+        for (uint32_t c = 0; c < nchunks; c++) {
+          const uint32_t i = c * 32 + lane;
+          const bool match = i < n && (m & s_meta[i].x) != 0;
+          const uint32_t w = __ballot_sync(0xffffffffu, match);
+          if (match) {
+            const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
+            const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+            st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+            if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+          }
+          base += __popc(w);
+        }
+        if (p.use_digest) dsum = warp_sum64(dsum);
       }
-      if (p.use_digest) dsum = warp_sum64(dsum);
     } else {
       // ================= general run: filter + unicast + interleaved ticks, two passes =================
       const uint32_t nchunks = (n + 31) >> 5;
@@ -505,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_MIN_CTAS_PER_SM) fanout_kernel
     if (n_ticks) {   // re-arm: one lane per slot writes its timer back (events/timer.go: ticker keeps running)
       const uint32_t slotmask = (J == 32 ? 0xffffffffu : ((1u << J) - 1u)) << (tk_slot * J);
       const uint32_t fired_here = __popc(tk_mask & slotmask);
-      if (tk_j == 0 && tk_slot < nslots && fired_here) {
+      if (TIMERS && tk_j == 0 && tk_slot < nslots && fired_here) {
         DevTimer* t = &p.timers[(size_t)s * K + tk_slot];
         uint4 na = cur_ta, nb = cur_tb;
         if (tk_flags & kTimerOneshot) nb.z = tk_flags & ~kTimerActive;
