@@ -56,7 +56,7 @@ struct cpbus {
   unsigned long long* d_desc_ready = nullptr;
   unsigned long long launch_seq = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
-  uint32_t hints = 1;                     // bit0: control blocks / timer slots evict_last in L2 (+3 % at 65,536 subscribers)
+  int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
   unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
   cudaEvent_t fold_done[kFoldSlots] = {};
@@ -129,9 +129,9 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     // Several waves of short-lived CTAs rather than one persistent wave: the hardware CTA scheduler
     // balances the two dies / SM speed spread for free (pure-store microbenchmark, scripts/write_ceiling.cu:
     // 6.0 TB/s with one resident wave, 6.9 TB/s with >= 32 CTAs per SM).  Per-CTA setup here is a descriptor
-    // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is 4-8 mailboxes per warp
-    // (65,536 subscribers: 4 per warp -> 90.9 % of peak vs 83.3 % persistent, 75.7 % at 1 per warp;
-    //  1,048,576 subscribers with timers: 8 per warp -> 87.0 % vs 83.1 % at 64 per warp).
+    // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is 2-16 mailboxes per warp
+    // (65,536 subscribers: 2-4 per warp -> 97 % of the copy peak, 1 per warp 89 %, persistent 83 %;
+    //  1,048,576 subscribers with timers: 8-16 per warp -> 94 %, 4 or 32 per warp 85 %).
     if (occ_smem != smem) {
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE, TIMERS>, kThreads, smem));
       occ_smem = smem;
@@ -139,7 +139,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     }
     const uint32_t need = (p.n_subs + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t spw = b->subs_per_warp;
-    if (!spw) spw = std::max(1u, std::min(8u, need / (uint32_t)(b->sm_count * 14)));
+    if (!spw) spw = std::max(1u, std::min(16u, (need + (uint32_t)b->sm_count * 7) / (uint32_t)(b->sm_count * 14)));
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
     (void)occ_blocks;
   }
@@ -157,7 +157,10 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
-  p.hints = b->hints;
+  // evict_last on control blocks / timer slots pays while they are a small slice of the 126 MB L2
+  // (65,536 subscribers, 2-4 MiB: +3 %); at 1,048,576 subscribers (64 MiB with timers) it costs 8 %.
+  const size_t hot_bytes = (size_t)b->n_next * (sizeof(SubCtl) + (p.timers_on ? b->K * sizeof(DevTimer) : 0));
+  p.hints = b->hints >= 0 ? (uint32_t)b->hints : (hot_bytes <= (16u << 20) ? 1u : 0u);
   const size_t smem = fanout_smem_bytes(p.smem_cap);
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
@@ -309,7 +312,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
-  if (const char* e = getenv("CPBUS_HINTS")) b->hints = (uint32_t)atoi(e);
+  if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);
   if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
   int rc = CPBUS_OK;
   auto fail = [&](int code) { cpbus_destroy(b); return code; };
@@ -349,7 +352,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   // rings are NOT cleared: a slot is only ever read after it has been written (head/tail bound every read)
   bool ok = cudaMemsetAsync(b->d_ctl, 0, N * sizeof(SubCtl), b->stream) == cudaSuccess &&
             cudaMemsetAsync(b->d_stats, 0, sizeof(DevStats), b->stream) == cudaSuccess &&
-            (!K || cudaMemsetAsync(b->d_timers, 0, N * K * sizeof(DevTimer), b->stream) == cudaSuccess) &&
+            (!K || cudaMemsetAsync(b->d_timers, 0xFF, N * K * sizeof(DevTimer), b->stream) == cudaSuccess) &&   // every slot idle
             cudaStreamSynchronize(b->stream) == cudaSuccess;
   if (!ok) return fail(CPBUS_ECUDA);
   {
@@ -446,7 +449,7 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
       HostTimer& t = b->h_timers[(size_t)l * b->K + k];
       if (t.active) { t.active = false; b->n_timers--; }
     }
-    CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K, 0, b->K * sizeof(DevTimer), b->stream));
+    CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K, 0xFF, b->K * sizeof(DevTimer), b->stream));
   }
   CK(cudaStreamSynchronize(b->stream));
   b->n_active--;
@@ -475,8 +478,7 @@ int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t so
     HostTimer& t = b->h_timers[(size_t)l * b->K + k];
     if (t.active) continue;
     t.active = true; t.oneshot = oneshot != 0; t.period = period_ns; t.next_due = b->now + period_ns; t.source_id = source_id;
-    DevTimer d{}; d.next_due = t.next_due; d.period = period_ns; d.source_id = source_id; d.fired = 0;
-    d.flags = kTimerActive | (oneshot ? kTimerOneshot : 0u);
+    DevTimer d{}; d.next_due = t.next_due; d.period = oneshot ? 0 : period_ns; d.source_id = source_id; d.fired = 0;
     CK(cudaMemcpyAsync(b->d_timers + (size_t)l * b->K + k, &d, sizeof(d), cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     b->n_timers++;
@@ -512,8 +514,7 @@ int cpbus_timer_add_many(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t pe
     t.active = true; t.oneshot = oneshot != 0; t.period = period_ns; t.next_due = b->now + period_ns;
     t.source_id = source_ids ? source_ids[i] : source_id0 + i;
     DevTimer& d = dev[(size_t)i * b->K];
-    d.next_due = t.next_due; d.period = period_ns; d.source_id = t.source_id; d.fired = 0;
-    d.flags = kTimerActive | (oneshot ? kTimerOneshot : 0u);
+    d.next_due = t.next_due; d.period = oneshot ? 0 : period_ns; d.source_id = t.source_id; d.fired = 0; d.pad[0] = d.pad[1] = 0;
     if (oneshot) b->oneshot_idx.push_back((size_t)(l0 + i) * b->K);
   }
   CK(cudaMemcpyAsync(b->d_timers + (size_t)l0 * b->K, dev.data(), dev.size() * sizeof(DevTimer), cudaMemcpyHostToDevice, b->stream));
@@ -534,7 +535,7 @@ int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
   HostTimer& t = b->h_timers[(size_t)l * b->K + k];
   if (!t.active) return CPBUS_ENOENT;
   t.active = false; b->n_timers--;
-  CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K + k, 0, sizeof(DevTimer), b->stream));
+  CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K + k, 0xFF, sizeof(DevTimer), b->stream));
   CK(cudaStreamSynchronize(b->stream));
   if (b->n_timers == 0) b->min_period = UINT64_MAX;
   return push_mask_words(b, l, 1);

@@ -23,7 +23,7 @@ namespace cpbus_dev {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef CPBUS_TIMERS_MIN_CTAS
-#define CPBUS_TIMERS_MIN_CTAS 3    // timers build: 80 registers, no spills
+#define CPBUS_TIMERS_MIN_CTAS 4    // timers build: 64 registers, no spills (hot/cold timer slot halves, stats in shared memory)
 #endif
 #ifndef CPBUS_TIMER_PREFETCH
 #define CPBUS_TIMER_PREFETCH 1
@@ -33,18 +33,20 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
-constexpr uint32_t kTimerActive = 1u, kTimerOneshot = 2u;
 constexpr uint64_t kDigestP = 0x9E3779B97F4A7C15ull;
 constexpr uint32_t kPowTableLen = 2048 + 65 + 7;   // batch_cap <= 2048
 
-struct __align__(32) DevTimer {     // one timer slot (events/timer.go: one goroutine + ticker)
+// One timer slot (events/timer.go: one goroutine + ticker).  The first 16 bytes are all the fan-out kernel
+// needs to decide whether anything fires (and are what it prefetches); the second half is touched only
+// when a tick is actually emitted.  Disarmed slot: next_due == kTimerIdle.  One-shot: period == 0.
+struct __align__(32) DevTimer {
   uint64_t next_due;
   uint64_t period;
   uint32_t source_id;
   uint32_t fired;
-  uint32_t flags;
-  uint32_t pad;
+  uint32_t pad[2];
 };
+constexpr uint64_t kTimerIdle = ~0ull;
 
 // Statistics are spread over kStatSlots sector-sized slots: same-address REDs serialise at
 // L2 (~2.7 ns each, measured: 65,536 warps -> +180 us per launch), distinct sectors do not.
@@ -132,7 +134,13 @@ __device__ __forceinline__ void st_record(cpbus_event* dst, const uint4& a, cons
 }
 // 32-byte sector load/store with an L2 eviction-priority hint (control blocks and timer slots are
 // re-read every launch; ring records are write-once streams)
-__device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, uint64_t pol, bool hinted) {
+__device__ __forceinline__ uint64_t keep_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, uint64_t, bool hinted) {
+  const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -142,12 +150,26 @@ __device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, u
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(src));
 }
-__device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4& b, uint64_t pol, bool hinted) {
+__device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4& b, uint64_t, bool hinted) {
+  const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
                  "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol)
                  : "memory");
   else st_v8(dst, a, b);
+}
+__device__ __forceinline__ void ld_half(const void* src, uint4& a, uint64_t, bool hinted) {
+  const uint64_t pol = hinted ? keep_policy() : 0ull;
+  if (hinted)
+    asm volatile("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src), "l"(pol));
+  else
+    asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src));
+}
+__device__ __forceinline__ void st_half(void* dst, const uint4& a, uint64_t, bool hinted) {
+  const uint64_t pol = hinted ? keep_policy() : 0ull;
+  if (hinted)
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "l"(pol) : "memory");
+  else st_v4(dst, a);
 }
 // TMA 1-D bulk copies (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
@@ -192,6 +214,7 @@ struct BatchSummary {
   uint32_t present;        // OR of codebits of the broadcast events
   uint32_t has_unicast;    // any record with a specific target
   uint32_t hist[32];       // broadcast events per code
+  uint32_t acc_deliv, acc_ticks, acc_over, acc_pad;   // per-CTA statistics (flushed once at exit)
   uint64_t red[kWarpsPerCta];
 };
 
@@ -220,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   const uint32_t n = p.n_ev;
 
   // ---- stage the batch: one elected thread drives the TMA engine ----
-  if (tid == 0) mbar_init(&s_sum->mbar, 1);
+  if (tid == 0) { mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_over = 0; }
   __syncthreads();
   if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
     const uint32_t pow_bytes = ((cap + 65u) * 8u + 15u) & ~15u;
@@ -236,13 +259,12 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   const bool timers_on = TIMERS && p.timers_on && K;
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
-  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca, tb = ca;
+  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
   const bool keep = p.hints & 1u;
-  uint64_t pol_keep = 0;
-  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  const uint64_t pol_keep = 0;   // the policy is materialised at each use (one instruction) rather than held in registers
   if (s < p.n_subs) {
     ld_sector(p.ctl + s, ca, cb, pol_keep, keep);
-    if (CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, ta, tb, pol_keep, keep);
+    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, pol_keep, keep);
   }
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
@@ -317,20 +339,17 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
   const uint32_t scratch_words = max(32u, cap / 2u);                   // per warp: 32 tick positions or cap u16 event indices
   uint32_t* my_tick = s_tick + warp * scratch_words;
-  unsigned long long acc_deliv = 0, acc_ticks = 0, acc_over = 0;
   bool bulk_pending = false;
 
   // software pipeline: the control block (and timer slot) of the NEXT subscriber is in flight
   // while the current one is being written, so no DRAM round trip is exposed per subscriber
   for (; s < p.n_subs; s += wstride) {
-    const uint4 cur_a = ca, cur_b = cb;
-    uint4 cur_ta = ta, cur_tb = tb;
-    if (!CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)s * K + tk_slot, cur_ta, cur_tb, pol_keep, keep);
+    const uint4 cur_a = ca, cur_b = cb, cur_ta = ta;
     {
       const uint32_t sn = s + wstride;
       if (sn < p.n_subs) {
         ld_sector(p.ctl + sn, ca, cb, pol_keep, keep);
-        if (CPBUS_TIMER_PREFETCH && timers_on && tk_slot < K) ld_sector(p.timers + (size_t)sn * K + tk_slot, ta, tb, pol_keep, keep);
+        if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)sn * K + tk_slot, ta, pol_keep, keep);
       }
     }
     const uint32_t m = cur_b.z;
@@ -345,18 +364,23 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     const bool dense = !has_unicast && ((m & present) == present);
 
     // ---- timers: which ticks fire in (previous watermark, w_now] ----
-    uint32_t n_ticks = 0, tk_mask = 0, tk_rank = 0, tk_src = 0, tk_fired = 0, tk_flags = 0;
-    bool tk_valid = false; uint64_t tk_due = 0, tk_period = 0, tk_due0 = 0;
+    uint32_t n_ticks = 0, tk_mask = 0, tk_rank = 0, tk_src = 0, tk_fired = 0;
+    bool tk_valid = false; uint64_t tk_due = 0, tk_period = 0;
     if (nslots) {
+      uint64_t tk_due0 = kTimerIdle;
       if (TIMERS && tk_slot < nslots) {
         tk_due0 = ((uint64_t)cur_ta.y << 32) | cur_ta.x; tk_period = ((uint64_t)cur_ta.w << 32) | cur_ta.z;
-        tk_src = cur_tb.x; tk_fired = cur_tb.y; tk_flags = cur_tb.z;
       }
       tk_due = tk_due0 + (uint64_t)tk_j * tk_period;
-      tk_valid = (tk_flags & kTimerActive) && tk_due <= p.w_now && (tk_j == 0 || !(tk_flags & kTimerOneshot));
+      tk_valid = tk_due0 != kTimerIdle && tk_due <= p.w_now && (tk_j == 0 || tk_period != 0);
       tk_mask = __ballot_sync(0xffffffffu, tk_valid);
       n_ticks = __popc(tk_mask);
       if (n_ticks) {
+        if (TIMERS && tk_slot < nslots) {   // cold half of the slot: only when something actually fires
+          uint4 cold;
+          ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
+          tk_src = cold.x; tk_fired = cold.y;
+        }
         // order simultaneous firings by (due, slot): rank = #valid ticks with a smaller key
         if (J == 32 || (tk_mask >> J) == 0) tk_rank = tk_j;       // only slot 0 fired
         else {
@@ -552,32 +576,33 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       const uint32_t slotmask = (J == 32 ? 0xffffffffu : ((1u << J) - 1u)) << (tk_slot * J);
       const uint32_t fired_here = __popc(tk_mask & slotmask);
       if (TIMERS && tk_j == 0 && tk_slot < nslots && fired_here) {
-        DevTimer* t = &p.timers[(size_t)s * K + tk_slot];
-        uint4 na = cur_ta, nb = cur_tb;
-        if (tk_flags & kTimerOneshot) nb.z = tk_flags & ~kTimerActive;
-        else { const uint64_t nd = tk_due0 + (uint64_t)fired_here * tk_period; na.x = (uint32_t)nd; na.y = (uint32_t)(nd >> 32); }
-        nb.y = tk_fired + fired_here;
-        st_sector(t, na, nb, pol_keep, keep);
+        unsigned char* t = reinterpret_cast<unsigned char*>(&p.timers[(size_t)s * K + tk_slot]);
+        // this lane has tk_j == 0, so tk_due is the slot's next_due as loaded
+        const uint64_t nd = tk_period ? tk_due + (uint64_t)fired_here * tk_period : kTimerIdle;   // one-shot disarms itself
+        st_half(t, make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), cur_ta.z, cur_ta.w), pol_keep, keep);
+        st_half(t + 16, make_uint4(tk_src, tk_fired + fired_here, 0u, 0u), pol_keep, keep);
       }
     }
     if (lane == 0 && k) {   // one full-sector write of the control block
       const uint64_t nt = tail + k;
       uint64_t nh = head;
-      if (!p.lossless && nt > p.ring_cap && nh < nt - p.ring_cap) { acc_over += nt - p.ring_cap - nh; nh = nt - p.ring_cap; }
+      if (!p.lossless && nt > p.ring_cap && nh < nt - p.ring_cap) { atomicAdd(&s_sum->acc_over, (uint32_t)(nt - p.ring_cap - nh)); nh = nt - p.ring_cap; }
       const uint64_t nd = p.use_digest ? dig * s_pow[k] + dsum : dig;
       st_sector(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), (uint32_t)nh, (uint32_t)(nh >> 32)),
                 make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u), pol_keep, keep);
-      acc_deliv += k; acc_ticks += n_ticks;
+      atomicAdd(&s_sum->acc_deliv, k);
+      if (TIMERS && n_ticks) atomicAdd(&s_sum->acc_ticks, n_ticks);
     }
   }
 
   if (STORE == CPBUS_STORE_BULK && bulk_pending && lane == 0)
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged batch must outlive the TMA reads
-  if (lane == 0) {
-    DevStatSlot* st = &p.stats->slot[(blockIdx.x * kWarpsPerCta + warp) % kStatSlots];
-    if (acc_deliv) atomicAdd(&st->deliveries, acc_deliv);
-    if (acc_ticks) atomicAdd(&st->ticks, acc_ticks);
-    if (acc_over) atomicAdd(&st->overwritten, acc_over);
+  __syncthreads();
+  if (tid == 0) {   // one RED per counter per CTA, spread over kStatSlots sectors
+    DevStatSlot* st = &p.stats->slot[blockIdx.x % kStatSlots];
+    if (s_sum->acc_deliv) atomicAdd(&st->deliveries, (unsigned long long)s_sum->acc_deliv);
+    if (s_sum->acc_ticks) atomicAdd(&st->ticks, (unsigned long long)s_sum->acc_ticks);
+    if (s_sum->acc_over) atomicAdd(&st->overwritten, (unsigned long long)s_sum->acc_over);
   }
 }
 
@@ -612,8 +637,8 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
   const uint32_t nslots = timers_on ? min((m >> kTimerHintShift) & 0xFu, K) : 0u;
   for (uint32_t t = 0; t < nslots; t++) {
     const DevTimer tm = timers[(size_t)s * K + t];
-    if ((tm.flags & kTimerActive) && tm.next_due <= w_now)
-      k += (tm.flags & kTimerOneshot) ? 1u : (w_now - tm.next_due) / tm.period + 1u;
+    if (tm.next_due != kTimerIdle && tm.next_due <= w_now)
+      k += tm.period ? (w_now - tm.next_due) / tm.period + 1u : 1u;
   }
   if (c.tail - c.head + k > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
 }
