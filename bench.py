@@ -329,9 +329,9 @@ def main():
                     trace_dev[slot * B: (slot + 1) * B].copy_(pinned[slot * B: (slot + 1) * B], non_blocking=True)
                 dist.broadcast(trace_dev[slot * B: (slot + 1) * B], src=0)
                 nat.check(bus.publish_device(trace_dev.data_ptr() + slot * B * 32, B, (i + 1) * B * DT_NS), "cpbus_publish_device")
-            tickets.append(bus.digest_fold_begin(rank * n_subs, n_subs))   # 32-byte D2H of the step's result, async
+            tickets.append(bus.step_result_begin())                   # 256-byte D2H of the step's result (written by the fan-out kernel)
             if len(tickets) > 2:
-                fold = bus.digest_fold_end(tickets.pop(0))            # ...read two steps later: the GPU never idles
+                fold = bus.step_result_end(tickets.pop(0))            # ...read two steps later: the GPU never idles
 
         if world > 1:
             # ts must keep increasing: restamp host copy for the e2e region
@@ -346,7 +346,7 @@ def main():
         for j in range(3):
             e2e_step(j)
         while tickets:
-            bus.digest_fold_end(tickets.pop(0))
+            bus.step_result_end(tickets.pop(0))
         nxt += 3
         barrier()
         s0 = bus.stats()
@@ -356,7 +356,7 @@ def main():
         for j in range(k2):
             e2e_step(j)
         while tickets:
-            fold = bus.digest_fold_end(tickets.pop(0))                # every step's result has reached the host
+            fold = bus.step_result_end(tickets.pop(0))                # every step's result has reached the host
         f1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - w0) * 1e3
@@ -366,10 +366,10 @@ def main():
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(d2, op=dist.ReduceOp.SUM)
         e2e = {"value": float(d2.item()) / (float(t2.item()) * 1e-3), "unit": "deliveries/s",
-               "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": 32, "steps": k2,
+               "h2d_bytes_per_step": B * 32, "d2h_bytes_per_step": 256, "steps": k2,
                "ms_per_step": float(t2.item()) / k2,
-               "api": "cpbus_advance+cpbus_publish(host events)+cpbus_flush+cpbus_digest_fold_begin/_end (result read 2 steps later)" if world == 1 else
-                      "pinned host batch -> H2D on rank 0 -> NCCL broadcast -> cpbus_publish_device + cpbus_digest_fold_begin/_end"}
+               "api": "cpbus_advance+cpbus_publish(host events)+cpbus_flush+cpbus_step_result_begin/_end (deliveries + digest checksum of the step, read 2 steps later)" if world == 1 else
+                      "pinned host batch -> H2D on rank 0 -> NCCL broadcast -> cpbus_publish_device + cpbus_step_result_begin/_end"}
         launches_e2e = s1["kernel_launches"] - s0["kernel_launches"]
     else:
         launches_e2e = 0

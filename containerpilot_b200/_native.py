@@ -76,6 +76,8 @@ SYMBOLS = {
     "cpbus_digest_fold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64 * 4)]),
     "cpbus_digest_fold_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint32)]),
     "cpbus_digest_fold_end": (C.c_int, [C.c_void_p, C.c_uint32, _P(C.c_uint64 * 4)]),
+    "cpbus_step_result_begin": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
+    "cpbus_step_result_end": (C.c_int, [C.c_void_p, C.c_uint32, _P(C.c_uint64 * 4)]),
     "cpbus_debug_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_stats": (C.c_int, [C.c_void_p, _P(Stats)]),
     "cpbus_device_ptrs": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_void_p)]),

@@ -154,6 +154,16 @@ class Bus:
         nat.check(self._lib.cpbus_digest_fold_end(self._h, ticket, C.byref(out)), "cpbus_digest_fold_end")
         return tuple(out)
 
+    def step_result_begin(self) -> int:
+        t = C.c_uint32()
+        nat.check(self._lib.cpbus_step_result_begin(self._h, C.byref(t)), "cpbus_step_result_begin")
+        return t.value
+
+    def step_result_end(self, ticket: int):
+        out = (C.c_uint64 * 4)()
+        nat.check(self._lib.cpbus_step_result_end(self._h, ticket, C.byref(out)), "cpbus_step_result_end")
+        return tuple(out)
+
     def debug_events(self):
         out = np.zeros(10, dtype=EVENT_DTYPE)
         n = C.c_size_t()

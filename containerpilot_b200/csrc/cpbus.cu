@@ -61,9 +61,17 @@ struct cpbus {
   unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
   cudaEvent_t fold_done[kFoldSlots] = {};
   uint32_t fold_next = 0;
-  cpbus_event* d_batch[2] = {nullptr, nullptr};
-  cpbus_event* h_batch[2] = {nullptr, nullptr};   // pinned staging
-  cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+  static constexpr int kStage = 4;         // staging ring: the host may run 3 flushes ahead of the GPU
+  cpbus_event* d_batch[kStage] = {};
+  cpbus_event* h_batch[kStage] = {};       // pinned staging
+  cudaEvent_t h2d_done[kStage] = {};       // on copy_stream: batch c has reached HBM
+  cudaEvent_t consumed[kStage] = {};       // on the bus stream: the fan-out that read d_batch[c] has finished
+  cudaStream_t copy_stream = nullptr;      // H2D of batch i+1 overlaps the fan-out of batch i
+  // per-launch results written by the fan-out kernel itself (no extra kernel to read a step's result)
+  DevResultSlot* d_result = nullptr;       // kResultRing x kResultSub slots
+  DevResultSlot* h_result = nullptr;       // pinned, kFoldSlots tickets x kResultSub
+  cudaEvent_t result_done[8] = {};
+  uint32_t result_next = 0;
   DevStats* h_stats = nullptr;            // pinned
   unsigned long long* h_fold = nullptr;   // pinned
   int cur = 0;
@@ -116,13 +124,13 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
   if (old != -1 && b->dbg_head == b->dbg_tail) b->dbg_tail = (b->dbg_tail + 1) % 10;
 }
 
-template <int STORE, bool TIMERS>
+template <int STORE, bool TIMERS, bool DIGEST>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done = false;   // per instantiation
   static size_t occ_smem = ~(size_t)0;
   static int occ_blocks = 1;
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   if (!grid) {
@@ -133,7 +141,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     // (65,536 subscribers: 2-4 per warp -> 97 % of the copy peak, 1 per warp 89 %, persistent 83 %;
     //  1,048,576 subscribers with timers: 8-16 per warp -> 94 %, 4 or 32 per warp 85 %).
     if (occ_smem != smem) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE, TIMERS>, kThreads, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE, TIMERS, DIGEST>, kThreads, smem));
       occ_smem = smem;
       if (occ_blocks < 1) occ_blocks = 1;
     }
@@ -143,7 +151,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
     (void)occ_blocks;
   }
-  fanout_kernel<STORE, TIMERS><<<grid, kThreads, smem, b->stream>>>(p);
+  fanout_kernel<STORE, TIMERS, DIGEST><<<grid, kThreads, smem, b->stream>>>(p);
   CK(cudaGetLastError());
   return CPBUS_OK;
 }
@@ -153,7 +161,9 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
-  p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w; p.n_ev = n;
+  p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w;
+  p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
+  p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
@@ -165,12 +175,20 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
-  const bool timers = p.timers_on != 0;
-  switch (b->store) {
-    case CPBUS_STORE_V4: rc = timers ? launch_fanout_t<CPBUS_STORE_V4, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_V4, false>(b, p, grid, smem); break;
-    case CPBUS_STORE_BULK: rc = timers ? launch_fanout_t<CPBUS_STORE_BULK, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_BULK, false>(b, p, grid, smem); break;
-    default: rc = timers ? launch_fanout_t<CPBUS_STORE_V8, true>(b, p, grid, smem) : launch_fanout_t<CPBUS_STORE_V8, false>(b, p, grid, smem); break;
+  const int variant = (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0);
+#define CPBUS_DISPATCH(ST)                                                         \
+  switch (variant) {                                                              \
+    case 0: rc = launch_fanout_t<ST, false, false>(b, p, grid, smem); break;      \
+    case 1: rc = launch_fanout_t<ST, false, true>(b, p, grid, smem); break;       \
+    case 2: rc = launch_fanout_t<ST, true, false>(b, p, grid, smem); break;       \
+    default: rc = launch_fanout_t<ST, true, true>(b, p, grid, smem); break;       \
   }
+  switch (b->store) {
+    case CPBUS_STORE_V4: CPBUS_DISPATCH(CPBUS_STORE_V4); break;
+    case CPBUS_STORE_BULK: CPBUS_DISPATCH(CPBUS_STORE_BULK); break;
+    default: CPBUS_DISPATCH(CPBUS_STORE_V8); break;
+  }
+#undef CPBUS_DISPATCH
   if (rc) return rc;
   b->st.batches++; b->st.kernel_launches++;
   b->last_watermark = w;
@@ -211,17 +229,22 @@ int flush_staged(cpbus* b, uint64_t w) {
   const uint32_t n = (uint32_t)b->n_staged;
   if (n == 0 && (b->n_timers == 0 || w == b->last_watermark)) return CPBUS_OK;
   const int c = b->cur;
-  if (n) CK(cudaMemcpyAsync(b->d_batch[c], b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->stream));
-  CK(cudaEventRecord(b->h2d_done[c], b->stream));
+  if (n) {
+    CK(cudaStreamWaitEvent(b->copy_stream, b->consumed[c], 0));   // the previous user of d_batch[c] is done
+    CK(cudaMemcpyAsync(b->d_batch[c], b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->copy_stream));
+    CK(cudaEventRecord(b->h2d_done[c], b->copy_stream));
+    CK(cudaStreamWaitEvent(b->stream, b->h2d_done[c], 0));
+  }
   bool ok = true;
   int rc = admit(b, b->d_batch[c], n, w, &ok);
   if (rc) return rc;
   if (!ok) return CPBUS_EAGAIN;   // staged events stay staged; drain and call flush again
   rc = launch_fanout(b, b->d_batch[c], n, w);
   if (rc) return rc;
+  CK(cudaEventRecord(b->consumed[c], b->stream));
   b->n_staged = 0;
-  b->cur ^= 1;
-  CK(cudaEventSynchronize(b->h2d_done[b->cur]));   // the buffer we are about to overwrite has left the host
+  b->cur = (b->cur + 1) % cpbus::kStage;
+  CK(cudaEventSynchronize(b->h2d_done[b->cur]));   // the pinned buffer we are about to overwrite has left the host
   return CPBUS_OK;
 }
 
@@ -339,11 +362,18 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32 * cpbus::kFoldSlots); ALLOC(b->d_pow, kPowTableLen * 8);
   ALLOC(b->d_desc, fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 128);
   if (cudaMemsetAsync(b->d_desc_ready, 0, 128, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
-  for (int i = 0; i < 2; i++) {
+  if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
+  for (int i = 0; i < cpbus::kStage; i++) {
     ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));
     if (cudaMallocHost((void**)&b->h_batch[i], (size_t)B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
     if (cudaEventCreateWithFlags(&b->h2d_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
+    if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   }
+  ALLOC(b->d_result, sizeof(DevResultSlot) * kResultRing * kResultSub);
+  if (cudaMemsetAsync(b->d_result, 0, sizeof(DevResultSlot) * kResultRing * kResultSub, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (cudaMallocHost((void**)&b->h_result, sizeof(DevResultSlot) * 8 * kResultSub) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  for (int i = 0; i < 8; i++)
+    if (cudaEventCreateWithFlags(&b->result_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
 #undef ALLOC
   if (cudaMallocHost((void**)&b->h_stats, sizeof(DevStats)) != cudaSuccess) return fail(CPBUS_ENOMEM);
   if (cudaMallocHost((void**)&b->h_fold, 32 * cpbus::kFoldSlots) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -377,11 +407,17 @@ int cpbus_destroy(cpbus_t* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->d_ring); cudaFree(b->d_ctl);
   cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
-  for (int i = 0; i < 2; i++) {
+  if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+  for (int i = 0; i < cpbus::kStage; i++) {
     cudaFree(b->d_batch[i]);
     if (b->h_batch[i]) cudaFreeHost(b->h_batch[i]);
     if (b->h2d_done[i]) cudaEventDestroy(b->h2d_done[i]);
+    if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  cudaFree(b->d_result);
+  if (b->h_result) cudaFreeHost(b->h_result);
+  for (int i = 0; i < 8; i++) if (b->result_done[i]) cudaEventDestroy(b->result_done[i]);
   if (b->h_stats) cudaFreeHost(b->h_stats);
   if (b->h_fold) cudaFreeHost(b->h_fold);
   for (int i = 0; i < cpbus::kFoldSlots; i++) if (b->fold_done[i]) cudaEventDestroy(b->fold_done[i]);
@@ -614,7 +650,9 @@ static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {
   SubCtl c{};
   CK(cudaMemcpyAsync(&c, b->d_ctl + l, sizeof(SubCtl), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
-  *tail = c.tail; *head = c.head;
+  *tail = c.tail;
+  // overwrite-oldest: the consumer's cursor can never be older than the oldest record still in the ring
+  *head = (!b->lossless && c.tail > b->R && c.tail - b->R > c.head) ? c.tail - b->R : c.head;
   return CPBUS_OK;
 }
 
@@ -707,6 +745,32 @@ int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4
   return rc ? rc : cpbus_digest_fold_end(b, ticket, out);
 }
 
+// The fan-out kernel leaves {deliveries, ticks, sum of the new digests} of each launch in a small ring;
+// reading a step's result therefore costs one 256-byte D2H and no extra kernel.
+int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) {
+  if (!b || !ticket) return CPBUS_EINVAL;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  const uint32_t t = b->result_next++ % 8;
+  const DevResultSlot* src = b->d_result + (size_t)(b->launch_seq % kResultRing) * kResultSub;
+  CK(cudaMemcpyAsync(b->h_result + (size_t)t * kResultSub, src, sizeof(DevResultSlot) * kResultSub, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaEventRecord(b->result_done[t], b->stream));
+  *ticket = t;
+  return CPBUS_OK;
+}
+
+int cpbus_step_result_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
+  if (!b || !out || ticket >= 8) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaEventSynchronize(b->result_done[ticket]));
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (int i = 0; i < kResultSub; i++) {
+    const DevResultSlot& r = b->h_result[(size_t)ticket * kResultSub + i];
+    out[0] += r.deliveries; out[1] += r.ticks; out[2] += r.digest_sum; out[3] += r.launch_seq;
+  }
+  return CPBUS_OK;
+}
+
 // DebugEvents — events/bus.go:34-54
 int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
@@ -728,14 +792,18 @@ int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
   if (!b || !out) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaMemsetAsync(&b->d_stats->overwritten, 0, sizeof(unsigned long long), b->stream));
+  if (!b->lossless && b->n_next) {
+    const uint32_t threads = 256, grid = std::min<uint32_t>((b->n_next + threads - 1) / threads, (uint32_t)b->sm_count * 4);
+    overwritten_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, b->n_next, b->R, &b->d_stats->overwritten);
+    CK(cudaGetLastError());
+  }
   CK(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   retire_oneshots(b, b->last_watermark);
-  b->st.deliveries = b->st.ticks = b->st.overwritten = 0;
-  for (int i = 0; i < kStatSlots; i++) {
-    b->st.deliveries += b->h_stats->slot[i].deliveries; b->st.ticks += b->h_stats->slot[i].ticks;
-    b->st.overwritten += b->h_stats->slot[i].overwritten;
-  }
+  b->st.deliveries = b->st.ticks = 0;
+  b->st.overwritten = b->h_stats->overwritten;
+  for (int i = 0; i < kStatSlots; i++) { b->st.deliveries += b->h_stats->slot[i].deliveries; b->st.ticks += b->h_stats->slot[i].ticks; }
   b->st.n_subs = b->n_active; b->st.n_timers = b->n_timers; b->st.now_ns = b->now;
   *out = b->st;
   return CPBUS_OK;

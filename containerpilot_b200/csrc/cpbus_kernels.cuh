@@ -51,10 +51,10 @@ constexpr uint64_t kTimerIdle = ~0ull;
 // Statistics are spread over kStatSlots sector-sized slots: same-address REDs serialise at
 // L2 (~2.7 ns each, measured: 65,536 warps -> +180 us per launch), distinct sectors do not.
 constexpr int kStatSlots = 256;
-struct __align__(32) DevStatSlot { unsigned long long deliveries, ticks, overwritten, pad; };
+struct __align__(32) DevStatSlot { unsigned long long deliveries, ticks, pad[2]; };
 struct DevStats {
   DevStatSlot slot[kStatSlots];
-  unsigned long long admit_overflow, pad[3];
+  unsigned long long admit_overflow, overwritten, pad[2];
 };
 
 // Per-subscriber control block: exactly one 32-byte sector, read once and written once
@@ -67,6 +67,11 @@ struct __align__(32) SubCtl {
   uint32_t pad;
 };
 
+// Per-launch result ring, filled by the fan-out kernel (kResultSub sector-sized sub-slots per launch so
+// that the per-CTA REDs do not serialise on one address; the host sums them).
+constexpr int kResultRing = 64, kResultSub = 8;
+struct __align__(32) DevResultSlot { unsigned long long deliveries, ticks, digest_sum, launch_seq; };
+
 struct FanoutParams {
   const cpbus_event* batch;   // n_ev records, sorted by ts (HBM)
   cpbus_event* ring;          // [n_subs][R]
@@ -77,6 +82,8 @@ struct FanoutParams {
   unsigned char* desc;        // per-launch batch descriptor, written by CTA 0, read by every other CTA
   unsigned long long* desc_ready;   // holds the launch_seq whose descriptor is complete
   unsigned long long launch_seq;
+  DevResultSlot* result;      // this launch's kResultSub sub-slots (zeroed by the previous launch)
+  DevResultSlot* result_next; // next launch's sub-slots: CTA 0 zeroes them
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -214,7 +221,8 @@ struct BatchSummary {
   uint32_t present;        // OR of codebits of the broadcast events
   uint32_t has_unicast;    // any record with a specific target
   uint32_t hist[32];       // broadcast events per code
-  uint32_t acc_deliv, acc_ticks, acc_over, acc_pad;   // per-CTA statistics (flushed once at exit)
+  uint32_t acc_deliv, acc_ticks, acc_pad[2];   // per-CTA statistics (flushed once at exit)
+  uint32_t acc_dig_lo, acc_dig_hi;                     // sum of fold32(new digest), as two 16-bit-limb sums (native 32-bit atomics)
   uint64_t red[kWarpsPerCta];
 };
 
@@ -227,7 +235,7 @@ __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
 
 // TIMERS=false compiles every timer/tick path out (the host knows when no timer is armed): fewer registers,
 // one more resident CTA per SM.
-template <int STORE, bool TIMERS>
+template <int STORE, bool TIMERS, bool DIGEST>
 __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPBUS_MIN_CTAS_PER_SM + 1) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   const uint32_t n = p.n_ev;
 
   // ---- stage the batch: one elected thread drives the TMA engine ----
-  if (tid == 0) { mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_over = 0; }
+  if (tid == 0) { mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0; }
   __syncthreads();
   if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
     const uint32_t pow_bytes = ((cap + 65u) * 8u + 15u) & ~15u;
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   uint4* g_desc = reinterpret_cast<uint4*>(p.desc);
   uint32_t* g_sum = reinterpret_cast<uint32_t*>(p.desc + (size_t)desc_words16 * 16u);
   if (blockIdx.x == 0) {
+    if (tid < kResultSub * 4) reinterpret_cast<unsigned long long*>(p.result_next)[tid] = 0ull;   // next launch's result slot
     if (tid == 0) { s_sum->present = 0; s_sum->has_unicast = 0; }
     if (tid < 32) s_sum->hist[tid] = 0;
     mbar_wait(&s_sum->mbar, 0);
@@ -355,7 +364,6 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     const uint32_t m = cur_b.z;
     if (!(m & kActiveBit)) continue;
     const uint64_t tail = ((uint64_t)cur_a.y << 32) | cur_a.x;
-    const uint64_t head = ((uint64_t)cur_a.w << 32) | cur_a.z;
     const uint64_t dig = ((uint64_t)cur_b.y << 32) | cur_b.x;
     cpbus_event* ring = p.ring + (size_t)s * p.ring_cap;
     const uint32_t gid = p.sub_base + s;
@@ -376,11 +384,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       tk_mask = __ballot_sync(0xffffffffu, tk_valid);
       n_ticks = __popc(tk_mask);
       if (n_ticks) {
-        if (TIMERS && tk_slot < nslots) {   // cold half of the slot: only when something actually fires
-          uint4 cold;
-          ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
-          tk_src = cold.x; tk_fired = cold.y;
-        }
+
         // order simultaneous firings by (due, slot): rank = #valid ticks with a smaller key
         if (J == 32 || (tk_mask >> J) == 0) tk_rank = tk_j;       // only slot 0 fired
         else {
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         }
       }
       k = n;
-      if (p.use_digest) dsum = s_q[n];
+      if (DIGEST) dsum = s_q[n];
     } else if (dense) {
       // ================= dense run with interleaved ticks: O(#ticks) bookkeeping =================
       if (tk_valid) my_tick[tk_rank] = tk_pos;
@@ -441,6 +445,11 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         const uint4 a = s4[2 * i], b = s4[2 * i + 1];
         st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
       }
+      if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
+        uint4 cold;
+        ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
+        tk_src = cold.x; tk_fired = cold.y;
+      }
       if (tk_valid) {
         const uint32_t out = tk_pos + tk_rank;
         const uint64_t w0 = (uint64_t)tk_fired + tk_j, w1 = tk_due;
@@ -449,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         const uint4 a = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
         const uint4 b = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
         st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-        if (p.use_digest) {
+        if (DIGEST) {
           // the run of events in front of this tick keeps its internal weights and is shifted by the
           // ticks still to come: (Q[pos_r] - Q[pos_{r-1}]) * P^(n_ticks - r)
           const uint32_t prev = tk_rank ? my_tick[tk_rank - 1] : 0u;
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
           if (tk_rank == n_ticks - 1) dsum += s_q[n] - s_q[tk_pos];
         }
       }
-      if (p.use_digest) dsum = warp_sum64(dsum);
+      if (DIGEST) dsum = warp_sum64(dsum);
       __syncwarp();
     } else if (!has_unicast && n_ticks == 0) {
       if constexpr (!TIMERS) {
@@ -484,9 +493,9 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
           const uint32_t i = my_idx[o];
           const uint4 a = s4[2 * i], b = s4[2 * i + 1];
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
-          if (p.use_digest) acc = acc * p32 + s_rhash[i];
+          if (DIGEST) acc = acc * p32 + s_rhash[i];
         }
-        if (p.use_digest) {
+        if (DIGEST) {
           // o is now the first index this lane did NOT write; its last one was o-32 (if any)
           dsum = (o >= 32 && o - 32 < k) ? acc * s_pow[k - 1 - (o - 32)] : 0ull;
           dsum = warp_sum64(dsum);
@@ -507,11 +516,11 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
             const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
             const uint4 a = s4[2 * i], b = s4[2 * i + 1];
             st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-            if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+            if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
           }
           base += __popc(w);
         }
-        if (p.use_digest) dsum = warp_sum64(dsum);
+        if (DIGEST) dsum = warp_sum64(dsum);
       }
     } else {
       // ================= general run: filter + unicast + interleaved ticks, two passes =================
@@ -555,7 +564,14 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
           for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= mrank) ? 1u : 0u;
           const uint4 a = s4[2 * i], b = s4[2 * i + 1];
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-          if (p.use_digest) dsum += s_rhash[i] * s_pow[k - 1 - out];
+          if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
+        }
+      }
+      if (n_ticks) {
+        if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
+          uint4 cold;
+          ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
+          tk_src = cold.x; tk_fired = cold.y;
         }
       }
       if (tk_valid) {   // the tick records themselves: {TimerExpired, name} (events/timer.go:31,60)
@@ -566,9 +582,9 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         const uint4 a = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
         const uint4 b = make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
         st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
-        if (p.use_digest) dsum += record_hash_words(w0, w1, w2, w3) * s_pow[k - 1 - out];
+        if (DIGEST) dsum += record_hash_words(w0, w1, w2, w3) * s_pow[k - 1 - out];
       }
-      if (p.use_digest) dsum = warp_sum64(dsum);
+      if (DIGEST) dsum = warp_sum64(dsum);
       __syncwarp();
     }
 
@@ -579,18 +595,21 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         unsigned char* t = reinterpret_cast<unsigned char*>(&p.timers[(size_t)s * K + tk_slot]);
         // this lane has tk_j == 0, so tk_due is the slot's next_due as loaded
         const uint64_t nd = tk_period ? tk_due + (uint64_t)fired_here * tk_period : kTimerIdle;   // one-shot disarms itself
-        st_half(t, make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), cur_ta.z, cur_ta.w), pol_keep, keep);
+        st_half(t, make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), (uint32_t)tk_period, (uint32_t)(tk_period >> 32)), pol_keep, keep);
         st_half(t + 16, make_uint4(tk_src, tk_fired + fired_here, 0u, 0u), pol_keep, keep);
       }
     }
     if (lane == 0 && k) {   // one full-sector write of the control block
       const uint64_t nt = tail + k;
-      uint64_t nh = head;
-      if (!p.lossless && nt > p.ring_cap && nh < nt - p.ring_cap) { atomicAdd(&s_sum->acc_over, (uint32_t)(nt - p.ring_cap - nh)); nh = nt - p.ring_cap; }
-      const uint64_t nd = p.use_digest ? dig * s_pow[k] + dsum : dig;
-      st_sector(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), (uint32_t)nh, (uint32_t)(nh >> 32)),
+      const uint64_t nd = DIGEST ? dig * s_pow[k] + dsum : dig;
+      st_sector(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), cur_a.z, cur_a.w),   // head: consumer-owned, passed through
                 make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u), pol_keep, keep);
       atomicAdd(&s_sum->acc_deliv, k);
+      if (DIGEST) {
+        const uint32_t f = (uint32_t)nd ^ (uint32_t)(nd >> 32);
+        atomicAdd(&s_sum->acc_dig_lo, f & 0xFFFFu);
+        atomicAdd(&s_sum->acc_dig_hi, f >> 16);
+      }
       if (TIMERS && n_ticks) atomicAdd(&s_sum->acc_ticks, n_ticks);
     }
   }
@@ -602,7 +621,11 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     DevStatSlot* st = &p.stats->slot[blockIdx.x % kStatSlots];
     if (s_sum->acc_deliv) atomicAdd(&st->deliveries, (unsigned long long)s_sum->acc_deliv);
     if (s_sum->acc_ticks) atomicAdd(&st->ticks, (unsigned long long)s_sum->acc_ticks);
-    if (s_sum->acc_over) atomicAdd(&st->overwritten, (unsigned long long)s_sum->acc_over);
+    DevResultSlot* rs = &p.result[blockIdx.x % kResultSub];
+    if (s_sum->acc_deliv) atomicAdd(&rs->deliveries, (unsigned long long)s_sum->acc_deliv);
+    if (s_sum->acc_ticks) atomicAdd(&rs->ticks, (unsigned long long)s_sum->acc_ticks);
+    if (s_sum->acc_dig_lo | s_sum->acc_dig_hi) atomicAdd(&rs->digest_sum, (unsigned long long)s_sum->acc_dig_lo + ((unsigned long long)s_sum->acc_dig_hi << 16));
+    if (blockIdx.x == 0) atomicAdd(&rs->launch_seq, p.launch_seq);
   }
 }
 
@@ -641,6 +664,18 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
       k += tm.period ? (w_now - tm.next_due) / tm.period + 1u : 1u;
   }
   if (c.tail - c.head + k > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
+}
+
+// Throughput mode: records that were overwritten before the consumer took them.  The fan-out kernel never
+// touches `head` (it is consumer-owned); what has been lost is derived: max(0, tail - ring_cap - head).
+__global__ void overwritten_kernel(const SubCtl* ctl, uint32_t n, uint32_t ring_cap, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const SubCtl c = ctl[i];
+    if (c.tail > ring_cap && c.tail - ring_cap > c.head) acc += c.tail - ring_cap - c.head;
+  }
+  acc = warp_sum64(acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // (count, digest) folds over a range of mailboxes: one 32-byte result instead of 16 B per subscriber

@@ -110,7 +110,8 @@ typedef struct cpbus_stats_t {
   uint64_t ticks;          /* timer records among the deliveries                  */
   uint64_t batches;        /* fan-out launches                                    */
   uint64_t kernel_launches;/* all kernels this bus launched                       */
-  uint64_t overwritten;    /* undrained records lost to overwrite-oldest          */
+  uint64_t overwritten;    /* undrained records currently lost to overwrite-oldest:
+                              sum over mailboxes of max(0, tail - ring_cap - head) */
   uint64_t published_by_code[CPBUS_N_CODES]; /* reconciliation of the Prometheus
                               `containerpilot_events` counter (events/bus.go:130-132) */
   uint32_t n_subs;         /* currently subscribed                                */
@@ -177,6 +178,13 @@ int cpbus_digest_fold(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t out
  * while step i+1 is already running. */
 int cpbus_digest_fold_begin(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint32_t* ticket);
 int cpbus_digest_fold_end(cpbus_t* bus, uint32_t ticket, uint64_t out[4]);
+
+/* Result of the LAST fan-out launch, written by the kernel itself: out = {records delivered by that launch,
+ * ticks among them, sum over every mailbox it appended to of fold32(new digest) with
+ * fold32(x) = low32(x ^ (x >> 32)), launch ordinal}.
+ * _begin enqueues a 256-byte D2H on the bus stream (up to 8 outstanding tickets), _end waits for it. */
+int cpbus_step_result_begin(cpbus_t* bus, uint32_t* ticket);
+int cpbus_step_result_end(cpbus_t* bus, uint32_t ticket, uint64_t out[4]);
 
 /* ---- observation ---- */
 /* DebugEvents (events/bus.go:34-54): drains the 10-slot ring of the last published

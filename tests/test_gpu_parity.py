@@ -245,3 +245,49 @@ def test_empty_and_ragged_batches():
             nat.check(bus.flush(), "flush")
         bus.sync()
         tr.compare(bus, orc, 5, window=64)
+
+
+def test_step_result_written_by_the_kernel():
+    """cpbus_step_result_begin/_end: the fan-out kernel leaves {deliveries, ticks, sum fold32(new digest), launch ordinal}
+    of every launch in a ring — checked against per-mailbox digests and the oracle's counts."""
+    n_subs = 777
+    rng = np.random.default_rng(9)
+    masks = np.where(rng.random(n_subs) < 0.5, nat.MASK_ALL, rng.integers(1, 1 << 17, n_subs)).astype(np.uint32)
+    orc = ob.Oracle(n_subs, timers_per_sub=1, keep_window=1024)
+    with Bus(n_subs, ring_cap=1024, batch_cap=256, timers_per_sub=1) as bus:
+        bus.subscribe_many(masks)
+        for m in masks:
+            orc.subscribe(int(m))
+        bus.timer_add_many(0, n_subs, 70_000, source_id0=100)
+        for s in range(n_subs):
+            orc.timer_add(s, 70_000, 100 + s, False)
+        prev_counts = np.zeros(n_subs, dtype=np.uint64)
+        now = 0
+        for step in range(6):
+            codes = rng.integers(0, 17, 200).astype(np.uint32); srcs = rng.integers(0, 50, 200).astype(np.uint32)
+            d0, t0 = orc.total_deliveries(), orc.total_ticks()
+            for c, s_ in zip(codes, srcs):
+                now += 1000
+                nat.check(bus.advance(now), "advance"); orc.advance(now)
+                nat.check(bus.publish(int(c), int(s_)), "publish"); orc.publish(int(c), int(s_))
+            nat.check(bus.flush(), "flush")
+            res = bus.step_result_end(bus.step_result_begin())
+            dig = bus.digests(0, n_subs)
+            touched = dig["count"] != prev_counts
+            fold = (dig["digest"] ^ (dig["digest"] >> np.uint64(32))) & np.uint64(0xFFFFFFFF)
+            assert res[0] == orc.total_deliveries() - d0 and res[1] == orc.total_ticks() - t0
+            assert res[2] == int(fold[touched].sum()) and res[3] == step + 1
+            prev_counts = dig["count"].copy()
+        tr.compare(bus, orc, n_subs)
+
+
+def test_drain_after_overwrite_reports_lost_records():
+    with Bus(2, ring_cap=64, batch_cap=32) as bus:
+        bus.subscribe(); bus.subscribe(1 << 3)
+        for i in range(200):
+            nat.check(bus.publish(1 + i % 4, i), "publish")
+        nat.check(bus.flush(), "flush")
+        assert bus.stats()["overwritten"] == (200 - 64) + 0      # mailbox 1 only took code 3: 50 records, nothing lost
+        got = bus.drain(0)
+        assert len(got) == 64 and list(got["source_id"]) == list(range(136, 200))
+        assert bus.stats()["overwritten"] == 0 and len(bus.drain(0)) == 0
