@@ -439,11 +439,18 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       if (tk_valid) my_tick[tk_rank] = tk_pos;
       __syncwarp();
       k = n + n_ticks;
-      for (uint32_t i = lane; i < n; i += 32) {
-        uint32_t out = i;
-        for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= i) ? 1u : 0u;
-        const uint4 a = s4[2 * i], b = s4[2 * i + 1];
-        st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+      // event i lands at i + #{ticks with pos <= i}.  Tick positions are sorted, so the count is warp-uniform for a
+      // whole 32-event chunk unless a tick falls strictly inside it (rare: 2-3 ticks per 256 events in config 3).
+      uint32_t t_idx = 0;
+      for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+        while (t_idx < n_ticks && my_tick[t_idx] <= c0) t_idx++;
+        const uint32_t i = c0 + lane;
+        uint32_t out = i + t_idx;
+        for (uint32_t t = t_idx; t < n_ticks && my_tick[t] < c0 + 32; t++) out += (my_tick[t] <= i) ? 1u : 0u;
+        if (i < n) {
+          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+        }
       }
       if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
         uint4 cold;
