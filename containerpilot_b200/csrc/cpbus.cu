@@ -127,8 +127,6 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
 template <int STORE, bool TIMERS, bool DIGEST>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done = false;   // per instantiation
-  static size_t occ_smem = ~(size_t)0;
-  static int occ_blocks = 1;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
@@ -140,16 +138,10 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     // copy + TMA wait (~2 us), so the sweet spot measured on the real kernel is 2-16 mailboxes per warp
     // (65,536 subscribers: 2-4 per warp -> 97 % of the copy peak, 1 per warp 89 %, persistent 83 %;
     //  1,048,576 subscribers with timers: 8-16 per warp -> 94 %, 4 or 32 per warp 85 %).
-    if (occ_smem != smem) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, fanout_kernel<STORE, TIMERS, DIGEST>, kThreads, smem));
-      occ_smem = smem;
-      if (occ_blocks < 1) occ_blocks = 1;
-    }
     const uint32_t need = (p.n_subs + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t spw = b->subs_per_warp;
     if (!spw) spw = std::max(1u, std::min(16u, (need + (uint32_t)b->sm_count * 7) / (uint32_t)(b->sm_count * 14)));
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
-    (void)occ_blocks;
   }
   fanout_kernel<STORE, TIMERS, DIGEST><<<grid, kThreads, smem, b->stream>>>(p);
   CK(cudaGetLastError());

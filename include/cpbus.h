@@ -146,7 +146,12 @@ int cpbus_timer_cancel(cpbus_t* bus, uint32_t timer_id);
 
 /* ---- the hot path: EventBus.Publish (events/bus.go:125-140) ---- */
 /* Stages n events; only code/source_id are read from ev (seq, ts, target, flags
- * are stamped by the bus).  Flushes automatically whenever batch_cap is reached. */
+ * are stamped by the bus).  Flushes automatically whenever batch_cap is reached.
+ * Lossless mode: if an automatic flush hits a full mailbox the call stops and returns
+ * CPBUS_EAGAIN; events before the one that triggered the flush are staged, that one and
+ * the rest are not (cpbus_stats.publishes tells how many were taken).  Publishing one
+ * event per call, as the Go bus does, makes the retry point unambiguous.  Admission is
+ * all-or-nothing per batch: nothing of a refused batch is delivered. */
 int cpbus_publish(cpbus_t* bus, const cpbus_event* ev, size_t n);
 /* Direct mailbox write, bypassing the filter (`job.Rx <- ev`, jobs/jobs.go:262;
  * Subscriber.Receive, events/subscriber.go:30).  Ordered with publishes. */

@@ -76,3 +76,27 @@ def test_product_never_touches_the_oracle():
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
                     txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                     assert "oracle_binding" not in txt and "libcpbus_oracle" not in txt and "orc_" not in txt, fn
+
+
+def test_create_rejects_bad_configs_before_touching_the_device():
+    """Argument validation is host logic: the same status codes with or without a GPU."""
+    lib = nat.load()
+    def create(**kw):
+        cfg = nat.Config(); cfg.n_max_subs = 8; cfg.device = -1
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        h = C.c_void_p()
+        rc = lib.cpbus_create(C.byref(cfg), C.byref(h))
+        if rc == 0:
+            lib.cpbus_destroy(h)
+        return rc
+    assert create(n_max_subs=0) == nat.EINVAL
+    assert create(ring_cap=1000) == nat.EINVAL            # not a power of two
+    assert create(ring_cap=32) == nat.EINVAL              # < 64
+    assert create(ring_cap=1024, batch_cap=1024) == nat.EINVAL   # > ring_cap / 2
+    assert create(ring_cap=1024, batch_cap=100) == nat.EINVAL    # not a multiple of 32
+    assert create(timers_per_sub=3) == nat.EINVAL
+    assert create(store_path=9) == nat.EINVAL
+    assert lib.cpbus_create(None, None) == nat.EINVAL
+    assert lib.cpbus_destroy(None) == nat.EINVAL
+    assert lib.cpbus_strerror(nat.EAGAIN).startswith(b"mailbox full")
