@@ -223,25 +223,59 @@ def main():
             trace_q[:, 0] = seq0 + cycle * n_ev
             trace_q[:, 1] = (seq0 + 1 + cycle * n_ev) * DT_NS
 
-    CHUNK = 64                                                         # batches per NCCL broadcast (512 KiB)
+    CHUNK = 64                                                         # batches per NCCL broadcast (512 KiB), fallback ingest only
     state = {"step": 0}
-
     chunk_events = []                                                  # CPBUS_BENCH_TRACE=1: per-1000-step device timing
 
+    # Multi-GPU ingest of the HBM-resident stream.  Preferred: the publisher's trace is peer-mapped (CUDA IPC over
+    # NVLink) and every shard's fan-out kernel pulls its batch itself (cpbus_publish_device_staged: CTA 0 reads the
+    # 8 KiB across the link, stages it locally) — no collective call on the data path.  Fallback: NCCL broadcast.
+    ingest_mode, peer_trace = "local", None
+    if world > 1:
+        ingest_mode = "nccl-broadcast"
+        if not os.environ.get("CPBUS_BENCH_NCCL_INGEST"):
+            try:
+                from torch.multiprocessing.reductions import reduce_tensor
+                box = [reduce_tensor(trace_dev) if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                if rank != 0:
+                    fn, fargs = box[0]
+                    peer_trace = fn(*fargs)                            # aliases rank 0's HBM through cudaIpcOpenMemHandle
+                    probe = torch.empty((1, 32), dtype=torch.uint8, device=dev)
+                    probe.copy_(peer_trace[:1]); torch.cuda.synchronize()   # makes torch enable P2P access dev -> publisher
+                ok_t = torch.tensor([1], device=dev)
+                dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+                if int(ok_t.item()) == 1:
+                    ingest_mode = "nvlink-peer-pull (fused into the fan-out kernel)"
+            except Exception as ex:                                    # pragma: no cover - depends on the box
+                print(f"[bench] peer mapping unavailable ({ex!r}); falling back to NCCL broadcast", file=sys.stderr)
+                peer_trace = None
+        src_ptr = (peer_trace if (peer_trace is not None and ingest_mode.startswith("nvlink")) else trace_dev).data_ptr()
+    else:
+        src_ptr = trace_dev.data_ptr()
+    fused = ingest_mode.startswith("nvlink")
+
     def run_steps(k: int, trace_chunks: bool = False):
-        """k fan-out steps from the HBM-resident trace (multi-GPU: NCCL broadcast of the event stream)."""
+        """k fan-out steps from the HBM-resident trace."""
         for j in range(k):
             if trace_chunks and j % 1000 == 0:
                 ev_ = torch.cuda.Event(enable_timing=True); ev_.record(stream); chunk_events.append((j, ev_, time.perf_counter()))
             i = state["step"]
             slot, cycle = i % n_trace_batches, i // n_trace_batches
             if slot == 0 and cycle > 0:
+                if fused:                                              # nobody may be reading while the publisher re-stamps
+                    torch.cuda.synchronize(); dist.barrier()
                 restamp(cycle)
-            if world > 1 and slot % CHUNK == 0:
+                if fused:
+                    torch.cuda.synchronize(); dist.barrier()
+            if world > 1 and not fused and slot % CHUNK == 0:
                 hi = min(slot + CHUNK, n_trace_batches)
                 dist.broadcast(trace_dev[slot * B: hi * B], src=0)
             wm = (i + 1) * B * DT_NS
-            nat.check(bus.publish_device(trace_dev.data_ptr() + slot * B * 32, B, wm), "cpbus_publish_device")
+            if fused:
+                nat.check(bus.publish_device_staged(src_ptr + slot * B * 32, B, wm), "cpbus_publish_device_staged")
+            else:
+                nat.check(bus.publish_device(src_ptr + slot * B * 32, B, wm), "cpbus_publish_device")
             state["step"] = i + 1
 
     def barrier():
@@ -408,7 +442,7 @@ def main():
             "config": {"workload": wl["desc"], "subscribers_per_gpu": n_subs, "subscribers_total": n_subs * world,
                        "events_per_step": B, "ring_cap": R, "record_bytes": 32, "mode": "overwrite-oldest throughput mode",
                        "digest": not args.no_digest, "timers_per_sub": K_timers, "warmup_settle_steps": settle, "store_path": args.store,
-                       "parallelism": f"subscriber shards x{world}" + (", NCCL broadcast of the event stream" if world > 1 else ""),
+                       "parallelism": f"subscriber shards x{world}" + (f", ingest: {ingest_mode}" if world > 1 else ""),
                        "l2": f"inputs larger than L2: {n_subs * R * 32 / 2**30:.1f} GiB of rings per GPU, "
                              f"{d_local * 32 / 2**20:.0f} MiB written per step vs 126 MB L2",
                        "trace": f"splitmix-seeded uniform codes 1..16, 4096 sources, {n_trace_batches} batches cycled with re-stamped seq/ts"},

@@ -119,6 +119,10 @@ class Bus:
     def publish_device(self, dev_ptr: int, n: int, watermark_ns: int) -> int:
         return self._lib.cpbus_publish_device(self._h, C.c_void_p(dev_ptr), n, watermark_ns)
 
+    def publish_device_staged(self, dev_ptr: int, n: int, watermark_ns: int) -> int:
+        """dev_ptr may be a peer-mapped pointer into another GPU's HBM (fused NVLink ingest)."""
+        return self._lib.cpbus_publish_device_staged(self._h, C.c_void_p(dev_ptr), n, watermark_ns)
+
     # -- consumer side -----------------------------------------------------
     def drain(self, sub_id: int, cap: int | None = None):
         cap = cap or self.ring_cap

@@ -55,6 +55,7 @@ struct cpbus {
   unsigned char* d_desc = nullptr;        // per-launch batch descriptor (CTA 0 writes, the others read)
   unsigned long long* d_desc_ready = nullptr;
   unsigned long long launch_seq = 0;
+  cpbus_event* d_batch_local = nullptr;    // staged ingest: CTA 0's local copy of a peer batch
   uint32_t subs_per_warp = 0;             // 0 = auto
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
@@ -149,13 +150,14 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
 }
 
 // fan out `n` records at d_src with watermark w (all checks done by the caller)
-int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w) {
+int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool staged = false) {
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
   p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w;
   p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
-  p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub; p.n_ev = n;
+  p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
+  p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
@@ -361,6 +363,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     if (cudaEventCreateWithFlags(&b->h2d_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
     if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   }
+  ALLOC(b->d_batch_local, (size_t)B * sizeof(cpbus_event));
   ALLOC(b->d_result, sizeof(DevResultSlot) * kResultRing * kResultSub);
   if (cudaMemsetAsync(b->d_result, 0, sizeof(DevResultSlot) * kResultRing * kResultSub, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaMallocHost((void**)&b->h_result, sizeof(DevResultSlot) * 8 * kResultSub) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -407,7 +410,7 @@ int cpbus_destroy(cpbus_t* b) {
     if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
-  cudaFree(b->d_result);
+  cudaFree(b->d_result); cudaFree(b->d_batch_local);
   if (b->h_result) cudaFreeHost(b->h_result);
   for (int i = 0; i < 8; i++) if (b->result_done[i]) cudaEventDestroy(b->result_done[i]);
   if (b->h_stats) cudaFreeHost(b->h_stats);
@@ -623,19 +626,31 @@ int cpbus_sync(cpbus_t* b) {
   return CPBUS_OK;
 }
 
-int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
+static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged) {
   if (!b || (!d_events && n) || n > b->B || ((uintptr_t)d_events & 31u)) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = flush_staged(b, b->now))) return rc;
   if (watermark_ns < b->now) return CPBUS_EORDER;
   if (watermark_ns - b->last_watermark > max_window(b)) return CPBUS_EORDER;
   bool ok = true;
+  if (staged && b->lossless) return CPBUS_EINVAL;   // admission would have to read the peer batch: not supported
   if ((rc = admit(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, &ok))) return rc;
   if (!ok) return CPBUS_EAGAIN;
   b->now = watermark_ns;
-  if ((rc = launch_fanout(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns))) return rc;
+  if ((rc = launch_fanout(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, staged))) return rc;
   b->st.publishes += n; b->seq += n;
   return CPBUS_OK;
+}
+
+int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
+  return publish_device_impl(b, d_events, n, watermark_ns, false);
+}
+
+// Multi-GPU ingest fused into the fan-out kernel: d_events may be a pointer into ANOTHER GPU's HBM (the publisher's
+// event stream, peer-mapped over NVLink).  CTA 0 pulls the batch across the link once, stages it in local HBM and
+// publishes it with the batch descriptor; no collective, no extra launch.
+int cpbus_publish_device_staged(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
+  return publish_device_impl(b, d_events, n, watermark_ns, true);
 }
 
 static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {

@@ -84,6 +84,8 @@ struct FanoutParams {
   unsigned long long launch_seq;
   DevResultSlot* result;      // this launch's kResultSub sub-slots (zeroed by the previous launch)
   DevResultSlot* result_next; // next launch's sub-slots: CTA 0 zeroes them
+  cpbus_event* batch_local;   // staged mode: CTA 0's local copy of a batch it pulled from a peer GPU
+  uint32_t staged;            // 1: `batch` may live in another GPU's HBM (NVLink peer mapping): only CTA 0 reads it
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -255,8 +257,11 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   __syncthreads();
   if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
     const uint32_t pow_bytes = ((cap + 65u) * 8u + 15u) & ~15u;
-    mbar_expect_tx(&s_sum->mbar, n * 32u + pow_bytes);
-    if (n) bulk_g2s(s_batch, p.batch, n * 32u, &s_sum->mbar);
+    // staged mode (multi-GPU ingest fused into the fan-out): the batch is in the publisher GPU's memory; CTA 0 pulls it
+    // over NVLink once and every other CTA takes CTA 0's local copy after the descriptor flag (second mbarrier phase)
+    const bool direct = n && !p.staged;
+    mbar_expect_tx(&s_sum->mbar, (direct ? n * 32u : 0u) + pow_bytes);
+    if (direct) bulk_g2s(s_batch, p.batch, n * 32u, &s_sum->mbar);
     bulk_g2s(s_pow, p.pow_table, pow_bytes, &s_sum->mbar);
   }
 
@@ -285,6 +290,16 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     if (tid < kResultSub * 4) reinterpret_cast<unsigned long long*>(p.result_next)[tid] = 0ull;   // next launch's result slot
     if (tid == 0) { s_sum->present = 0; s_sum->has_unicast = 0; }
     if (tid < 32) s_sum->hist[tid] = 0;
+    if (p.staged && n) {   // peer pull: plain 16-byte loads on the NVLink-mapped pointer, into shared memory and the local copy
+      const uint4* src = reinterpret_cast<const uint4*>(p.batch);
+      uint4* loc = reinterpret_cast<uint4*>(p.batch_local);
+      uint4* dst = reinterpret_cast<uint4*>(s_batch);
+      for (uint32_t i = tid; i < 2 * n; i += kThreads) {
+        uint4 v;
+        asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        dst[i] = v; loc[i] = v;
+      }
+    }
     mbar_wait(&s_sum->mbar, 0);
     __syncthreads();
     {
@@ -335,11 +350,17 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       unsigned long long seen;
       do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.desc_ready) : "memory"); } while (seen < p.launch_seq);
     }
+    if (p.staged && n && tid == 0) {
+      mbar_wait(&s_sum->mbar, 0);                                    // phase 0 (power table) is over
+      asm volatile("fence.proxy.async;" ::: "memory");               // CTA 0's generic-proxy stores -> our async-proxy read
+      mbar_expect_tx(&s_sum->mbar, n * 32u);
+      bulk_g2s(s_batch, p.batch_local, n * 32u, &s_sum->mbar);
+    }
     __syncthreads();
     for (uint32_t i = tid; i < desc_words16; i += kThreads) s_desc[i] = __ldcg(g_desc + i);
     if (tid < 32) s_sum->hist[tid] = __ldcg(g_sum + 2 + tid);
     if (tid == 0) { s_sum->present = __ldcg(g_sum); s_sum->has_unicast = __ldcg(g_sum + 1); }
-    mbar_wait(&s_sum->mbar, 0);
+    mbar_wait(&s_sum->mbar, (p.staged && n) ? 1u : 0u);
     __syncthreads();
   }
   const uint32_t present = s_sum->present;

@@ -167,6 +167,12 @@ int cpbus_sync(cpbus_t* bus);
  * (seq/ts/target/flags set by the producer), sorted by ts_ns, n <= batch_cap,
  * 32-byte aligned.  watermark_ns >= last ts; becomes the bus clock. */
 int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
+/* Same, but d_events may point into ANOTHER GPU's HBM (the publisher's event stream, peer-mapped over
+ * NVLink, e.g. through CUDA IPC): one CTA of the fan-out kernel pulls the batch across the link, stages it
+ * locally and hands it to the other CTAs together with the batch descriptor — the broadcast of SURVEY.md §8e
+ * fused into the fan-out launch, no collective call.  The caller guarantees the peer batch is complete and
+ * stable while the launch runs (throughput mode only). */
+int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
 
 /* ---- consumer side ---- */
 /* Mailbox -> host, FIFO (`<-sub.Rx`).  *lost = records overwritten before they

@@ -291,3 +291,28 @@ def test_drain_after_overwrite_reports_lost_records():
         got = bus.drain(0)
         assert len(got) == 64 and list(got["source_id"]) == list(range(136, 200))
         assert bus.stats()["overwritten"] == 0 and len(bus.drain(0)) == 0
+
+
+def test_staged_ingest_is_bit_identical():
+    """cpbus_publish_device_staged (CTA 0 pulls the batch, stages it locally, the other CTAs read the staged copy):
+    same mailboxes as the direct path.  On one GPU the 'peer' pointer is simply local."""
+    import torch
+    n_subs, n_events, B = 5000, 2048, 256
+    rng = np.random.default_rng(31)
+    masks = np.where(rng.random(n_subs) < 0.6, nat.MASK_ALL, rng.integers(1, 1 << 17, n_subs)).astype(np.uint32)
+    codes = rng.integers(0, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 99, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs, timers_per_sub=1, keep_window=1024)
+    for s, m in enumerate(masks):
+        orc.subscribe(int(m)); orc.timer_add(s, 333_000, 7000 + s, False)
+    assert orc.publish_many(codes, srcs, dt_ns=10_000) == 0
+    ev = np.zeros(n_events, dtype=EVENT_DTYPE)
+    ev["seq"] = np.arange(n_events); ev["ts_ns"] = (np.arange(n_events) + 1) * 10_000
+    ev["code"], ev["source_id"], ev["target"] = codes, srcs, nat.TARGET_ALL
+    dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32)).cuda()
+    with Bus(n_subs, ring_cap=1024, batch_cap=B, timers_per_sub=1, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        bus.subscribe_many(masks)
+        bus.timer_add_many(0, n_subs, 333_000, source_id0=7000)
+        for i in range(0, n_events, B):
+            nat.check(bus.publish_device_staged(dev.data_ptr() + i * 32, B, (i + B) * 10_000), "cpbus_publish_device_staged")
+        bus.sync()
+        tr.compare(bus, orc, n_subs)
