@@ -183,7 +183,7 @@ def main():
     K_timers = 1 if wl["timers"] else 0
 
     # ---- synthetic trace, resident in HBM (rank 0 is the publisher's GPU) ----
-    n_trace_batches = min(steps + warmup, 4096)        # cycled; 4096 x 8 KiB = 32 MiB
+    n_trace_batches = min(steps + warmup, 16384)       # cycled; 16384 x 8 KiB = 128 MiB
     n_ev = n_trace_batches * B
     g = torch.Generator(device="cpu"); g.manual_seed(0xC0DEB200 + 2)
     if wl["zipf"]:
@@ -235,14 +235,22 @@ def main():
         ingest_mode = "nccl-broadcast"
         if not os.environ.get("CPBUS_BENCH_NCCL_INGEST"):
             try:
-                from torch.multiprocessing.reductions import reduce_tensor
-                box = [reduce_tensor(trace_dev) if rank == 0 else None]
+                # the publisher's stream lives in a cpbus_shared_alloc buffer; the other ranks map it (CUDA IPC, NVLink)
+                box = [None]
+                if rank == 0:
+                    shared_ptr, handle = bus.shared_alloc(n_ev * 32)
+
+                    class _Raw:                                        # zero-copy torch view of the shared buffer
+                        __cuda_array_interface__ = {"shape": (n_ev, 32), "typestr": "|u1", "data": (shared_ptr, False), "version": 2}
+                    shared_view = torch.as_tensor(_Raw(), device=dev)
+                    shared_view.copy_(trace_dev)
+                    trace_dev = shared_view
+                    trace_q = trace_dev.view(torch.int64).view(n_ev, 4)
+                    torch.cuda.synchronize()
+                    box = [handle]
                 dist.broadcast_object_list(box, src=0)
                 if rank != 0:
-                    fn, fargs = box[0]
-                    peer_trace = fn(*fargs)                            # aliases rank 0's HBM through cudaIpcOpenMemHandle
-                    probe = torch.empty((1, 32), dtype=torch.uint8, device=dev)
-                    probe.copy_(peer_trace[:1]); torch.cuda.synchronize()   # makes torch enable P2P access dev -> publisher
+                    peer_trace = bus.shared_open(box[0])
                 ok_t = torch.tensor([1], device=dev)
                 dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
                 if int(ok_t.item()) == 1:
@@ -250,7 +258,7 @@ def main():
             except Exception as ex:                                    # pragma: no cover - depends on the box
                 print(f"[bench] peer mapping unavailable ({ex!r}); falling back to NCCL broadcast", file=sys.stderr)
                 peer_trace = None
-        src_ptr = (peer_trace if (peer_trace is not None and ingest_mode.startswith("nvlink")) else trace_dev).data_ptr()
+        src_ptr = peer_trace if (peer_trace is not None and ingest_mode.startswith("nvlink")) else trace_dev.data_ptr()
     else:
         src_ptr = trace_dev.data_ptr()
     fused = ingest_mode.startswith("nvlink")
@@ -273,7 +281,9 @@ def main():
                 dist.broadcast(trace_dev[slot * B: hi * B], src=0)
             wm = (i + 1) * B * DT_NS
             if fused:
-                nat.check(bus.publish_device_staged(src_ptr + slot * B * 32, B, wm), "cpbus_publish_device_staged")
+                nslot = (slot + 1) % n_trace_batches                   # next batch: pulled by THIS launch, hidden under its stores
+                nxt_ptr = src_ptr + nslot * B * 32 if nslot else 0     # (not across a re-stamp boundary)
+                nat.check(bus.publish_device_staged(src_ptr + slot * B * 32, B, wm, nxt_ptr, B if nxt_ptr else 0), "cpbus_publish_device_staged")
             else:
                 nat.check(bus.publish_device(src_ptr + slot * B * 32, B, wm), "cpbus_publish_device")
             state["step"] = i + 1

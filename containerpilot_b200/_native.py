@@ -70,7 +70,10 @@ SYMBOLS = {
     "cpbus_flush": (C.c_int, [C.c_void_p]),
     "cpbus_sync": (C.c_int, [C.c_void_p]),
     "cpbus_publish_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),
-    "cpbus_publish_device_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),
+    "cpbus_publish_device_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "cpbus_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_void_p), C.c_char_p]),
+    "cpbus_shared_open": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_void_p)]),
+    "cpbus_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpbus_drain": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_uint64)]),
     "cpbus_peek_window": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_digest": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),

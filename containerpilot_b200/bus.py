@@ -119,9 +119,24 @@ class Bus:
     def publish_device(self, dev_ptr: int, n: int, watermark_ns: int) -> int:
         return self._lib.cpbus_publish_device(self._h, C.c_void_p(dev_ptr), n, watermark_ns)
 
-    def publish_device_staged(self, dev_ptr: int, n: int, watermark_ns: int) -> int:
-        """dev_ptr may be a peer-mapped pointer into another GPU's HBM (fused NVLink ingest)."""
-        return self._lib.cpbus_publish_device_staged(self._h, C.c_void_p(dev_ptr), n, watermark_ns)
+    def publish_device_staged(self, dev_ptr: int, n: int, watermark_ns: int, next_ptr: int = 0, next_n: int = 0) -> int:
+        """dev_ptr / next_ptr may be peer-mapped pointers into another GPU's HBM (fused NVLink ingest)."""
+        return self._lib.cpbus_publish_device_staged(self._h, C.c_void_p(dev_ptr), n, watermark_ns,
+                                                     C.c_void_p(next_ptr) if next_ptr else None, next_n)
+
+    def shared_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a new buffer on this bus's GPU, mappable by the other GPUs."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        nat.check(self._lib.cpbus_shared_alloc(self._h, nbytes, C.byref(ptr), handle), "cpbus_shared_alloc")
+        return ptr.value, handle.raw
+
+    def shared_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        nat.check(self._lib.cpbus_shared_open(self._h, handle, C.byref(ptr)), "cpbus_shared_open")
+        return ptr.value
+
+    def shared_close(self, ptr: int):
+        nat.check(self._lib.cpbus_shared_close(self._h, C.c_void_p(ptr)), "cpbus_shared_close")
 
     # -- consumer side -----------------------------------------------------
     def drain(self, sub_id: int, cap: int | None = None):

@@ -56,6 +56,11 @@ struct cpbus {
   unsigned long long* d_desc_ready = nullptr;
   unsigned long long launch_seq = 0;
   cpbus_event* d_batch_local = nullptr;    // staged ingest: CTA 0's local copy of a peer batch
+  cpbus_event* d_prefetch[2] = {nullptr, nullptr};   // fused ingest: next batch, pulled by the previous launch
+  const void* prefetched_ptr = nullptr;    // which peer batch sits in d_prefetch[prefetch_cur]
+  size_t prefetched_n = 0;
+  int prefetch_cur = 0;
+  std::vector<void*> shared_owned, shared_mapped;   // cpbus_shared_alloc / cpbus_shared_open
   uint32_t subs_per_warp = 0;             // 0 = auto
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
@@ -150,14 +155,16 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
 }
 
 // fan out `n` records at d_src with watermark w (all checks done by the caller)
-int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool staged = false) {
+int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool staged = false,
+                  const cpbus_event* prefetch_src = nullptr, cpbus_event* prefetch_dst = nullptr, uint32_t prefetch_n = 0) {
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
   p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w;
   p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
   p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
-  p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u; p.n_ev = n;
+  p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u;
+  p.prefetch_src = prefetch_src; p.prefetch_dst = prefetch_dst; p.prefetch_n = prefetch_n; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
@@ -364,6 +371,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   }
   ALLOC(b->d_batch_local, (size_t)B * sizeof(cpbus_event));
+  ALLOC(b->d_prefetch[0], (size_t)B * sizeof(cpbus_event)); ALLOC(b->d_prefetch[1], (size_t)B * sizeof(cpbus_event));
   ALLOC(b->d_result, sizeof(DevResultSlot) * kResultRing * kResultSub);
   if (cudaMemsetAsync(b->d_result, 0, sizeof(DevResultSlot) * kResultRing * kResultSub, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaMallocHost((void**)&b->h_result, sizeof(DevResultSlot) * 8 * kResultSub) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -410,7 +418,9 @@ int cpbus_destroy(cpbus_t* b) {
     if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
-  cudaFree(b->d_result); cudaFree(b->d_batch_local);
+  cudaFree(b->d_result); cudaFree(b->d_batch_local); cudaFree(b->d_prefetch[0]); cudaFree(b->d_prefetch[1]);
+  for (void* p : b->shared_mapped) cudaIpcCloseMemHandle(p);
+  for (void* p : b->shared_owned) cudaFree(p);
   if (b->h_result) cudaFreeHost(b->h_result);
   for (int i = 0; i < 8; i++) if (b->result_done[i]) cudaEventDestroy(b->result_done[i]);
   if (b->h_stats) cudaFreeHost(b->h_stats);
@@ -626,31 +636,81 @@ int cpbus_sync(cpbus_t* b) {
   return CPBUS_OK;
 }
 
-static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged) {
-  if (!b || (!d_events && n) || n > b->B || ((uintptr_t)d_events & 31u)) return CPBUS_EINVAL;
+static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged,
+                               const void* d_next, size_t n_next) {
+  if (!b || (!d_events && n) || n > b->B || ((uintptr_t)d_events & 31u) || n_next > b->B || ((uintptr_t)d_next & 31u)) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = flush_staged(b, b->now))) return rc;
   if (watermark_ns < b->now) return CPBUS_EORDER;
   if (watermark_ns - b->last_watermark > max_window(b)) return CPBUS_EORDER;
-  bool ok = true;
   if (staged && b->lossless) return CPBUS_EINVAL;   // admission would have to read the peer batch: not supported
+  bool ok = true;
   if ((rc = admit(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, &ok))) return rc;
   if (!ok) return CPBUS_EAGAIN;
   b->now = watermark_ns;
-  if ((rc = launch_fanout(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, staged))) return rc;
+  const cpbus_event* src = (const cpbus_event*)d_events;
+  if (staged && n && b->prefetched_ptr == d_events && b->prefetched_n == n) {
+    src = b->d_prefetch[b->prefetch_cur];   // the previous launch already pulled this batch over NVLink: plain local launch
+    staged = false;
+  }
+  const cpbus_event* pf_src = nullptr; cpbus_event* pf_dst = nullptr;
+  if (d_next && n_next) { pf_src = (const cpbus_event*)d_next; pf_dst = b->d_prefetch[b->prefetch_cur ^ 1]; }
+  if ((rc = launch_fanout(b, src, (uint32_t)n, watermark_ns, staged, pf_src, pf_dst, (uint32_t)n_next))) return rc;
+  if (pf_src) { b->prefetch_cur ^= 1; b->prefetched_ptr = d_next; b->prefetched_n = n_next; }
+  else { b->prefetched_ptr = nullptr; b->prefetched_n = 0; }
   b->st.publishes += n; b->seq += n;
   return CPBUS_OK;
 }
 
 int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
-  return publish_device_impl(b, d_events, n, watermark_ns, false);
+  return publish_device_impl(b, d_events, n, watermark_ns, false, nullptr, 0);
 }
 
-// Multi-GPU ingest fused into the fan-out kernel: d_events may be a pointer into ANOTHER GPU's HBM (the publisher's
-// event stream, peer-mapped over NVLink).  CTA 0 pulls the batch across the link once, stages it in local HBM and
-// publishes it with the batch descriptor; no collective, no extra launch.
-int cpbus_publish_device_staged(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
-  return publish_device_impl(b, d_events, n, watermark_ns, true);
+// Multi-GPU ingest fused into the fan-out kernel: d_events (and d_next) may point into ANOTHER GPU's HBM (the
+// publisher's event stream, peer-mapped over NVLink).  One CTA pulls the batch across the link, stages it in local
+// HBM and publishes it with the batch descriptor; if the caller names the NEXT batch, that one is pulled by the
+// same launch while its stores are in flight, so the following call starts from local memory.  No collective.
+int cpbus_publish_device_staged(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, const void* d_next, size_t n_next) {
+  return publish_device_impl(b, d_events, n, watermark_ns, true, d_next, n_next);
+}
+
+// ---- buffers shared between the GPUs of one box (CUDA IPC; NVLink peer mapping on the importing side) ----
+int cpbus_shared_alloc(cpbus_t* b, size_t bytes, void** dptr, unsigned char handle[64]) {
+  if (!b || !dptr || !handle || !bytes) return CPBUS_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  int rc = dev_guard(b); if (rc) return rc;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(%zu) failed", bytes); return CPBUS_ENOMEM; }
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return CPBUS_ECUDA; }
+  memcpy(handle, &h, 64);
+  b->shared_owned.push_back(p);
+  *dptr = p;
+  return CPBUS_OK;
+}
+
+int cpbus_shared_open(cpbus_t* b, const unsigned char handle[64], void** dptr) {
+  if (!b || !dptr || !handle) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;      // the IMPORTING device must be current: the mapping is made for it
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  b->shared_mapped.push_back(p);
+  *dptr = p;
+  return CPBUS_OK;
+}
+
+int cpbus_shared_close(cpbus_t* b, void* dptr) {
+  if (!b || !dptr) return CPBUS_EINVAL;
+  int rc = dev_guard(b); if (rc) return rc;
+  CK(cudaStreamSynchronize(b->stream));
+  for (size_t i = 0; i < b->shared_owned.size(); i++)
+    if (b->shared_owned[i] == dptr) { cudaFree(dptr); b->shared_owned.erase(b->shared_owned.begin() + i); return CPBUS_OK; }
+  for (size_t i = 0; i < b->shared_mapped.size(); i++)
+    if (b->shared_mapped[i] == dptr) { cudaIpcCloseMemHandle(dptr); b->shared_mapped.erase(b->shared_mapped.begin() + i); return CPBUS_OK; }
+  return CPBUS_ENOENT;
 }
 
 static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {

@@ -86,6 +86,9 @@ struct FanoutParams {
   DevResultSlot* result_next; // next launch's sub-slots: CTA 0 zeroes them
   cpbus_event* batch_local;   // staged mode: CTA 0's local copy of a batch it pulled from a peer GPU
   uint32_t staged;            // 1: `batch` may live in another GPU's HBM (NVLink peer mapping): only CTA 0 reads it
+  const cpbus_event* prefetch_src;   // next batch in the publisher GPU's HBM (peer pointer) or nullptr
+  cpbus_event* prefetch_dst;         // local buffer it is pulled into while this launch's stores are in flight
+  uint32_t prefetch_n;
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -345,6 +348,15 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     __threadfence();
     __syncthreads();
     if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
+    if (p.prefetch_src) {   // fused ingest: pull the NEXT batch across NVLink now; the transfer hides under this launch's stores
+      const uint4* src = reinterpret_cast<const uint4*>(p.prefetch_src);
+      uint4* dst = reinterpret_cast<uint4*>(p.prefetch_dst);
+      for (uint32_t i = tid; i < 2 * p.prefetch_n; i += kThreads) {
+        uint4 v;
+        asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        dst[i] = v;
+      }
+    }
   } else {
     if (tid == 0) {
       unsigned long long seen;

@@ -170,9 +170,20 @@ int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t 
 /* Same, but d_events may point into ANOTHER GPU's HBM (the publisher's event stream, peer-mapped over
  * NVLink, e.g. through CUDA IPC): one CTA of the fan-out kernel pulls the batch across the link, stages it
  * locally and hands it to the other CTAs together with the batch descriptor — the broadcast of SURVEY.md §8e
- * fused into the fan-out launch, no collective call.  The caller guarantees the peer batch is complete and
- * stable while the launch runs (throughput mode only). */
-int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
+ * fused into the fan-out launch, no collective call.  If d_next/n_next name the FOLLOWING batch, the same launch
+ * also pulls it (the NVLink transfer hides under this launch's stores) and the next call, given that pointer as its
+ * d_events, starts from local memory.  The caller guarantees the peer batches are complete and stable while the
+ * launch runs (throughput mode only). */
+int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns,
+                                const void* d_next, size_t n_next);
+
+/* Buffers shared between the GPUs (processes) of one box, for the publisher's event stream: _alloc makes a
+ * device buffer on this bus's GPU and returns a 64-byte CUDA IPC handle; _open, called on ANOTHER bus (another
+ * process/GPU), maps it over NVLink and returns a pointer valid for cpbus_publish_device_staged there.
+ * _close frees (owner) or unmaps (importer); cpbus_destroy closes what is left. */
+int cpbus_shared_alloc(cpbus_t* bus, size_t bytes, void** dptr, unsigned char handle[64]);
+int cpbus_shared_open(cpbus_t* bus, const unsigned char handle[64], void** dptr);
+int cpbus_shared_close(cpbus_t* bus, void* dptr);
 
 /* ---- consumer side ---- */
 /* Mailbox -> host, FIFO (`<-sub.Rx`).  *lost = records overwritten before they
