@@ -348,15 +348,6 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     __threadfence();
     __syncthreads();
     if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
-    if (p.prefetch_src) {   // fused ingest: pull the NEXT batch across NVLink now; the transfer hides under this launch's stores
-      const uint4* src = reinterpret_cast<const uint4*>(p.prefetch_src);
-      uint4* dst = reinterpret_cast<uint4*>(p.prefetch_dst);
-      for (uint32_t i = tid; i < 2 * p.prefetch_n; i += kThreads) {
-        uint4 v;
-        asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
-        dst[i] = v;
-      }
-    }
   } else {
     if (tid == 0) {
       unsigned long long seen;
@@ -666,6 +657,17 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     if (s_sum->acc_ticks) atomicAdd(&rs->ticks, (unsigned long long)s_sum->acc_ticks);
     if (s_sum->acc_dig_lo | s_sum->acc_dig_hi) atomicAdd(&rs->digest_sum, (unsigned long long)s_sum->acc_dig_lo + ((unsigned long long)s_sum->acc_dig_hi << 16));
     if (blockIdx.x == 0) atomicAdd(&rs->launch_seq, p.launch_seq);
+  }
+  if (blockIdx.x == 0 && p.prefetch_src) {
+    // fused ingest: CTA 0 is done with its own mailboxes; pull the NEXT batch across NVLink now.  The link round trip
+    // hides under the stores of the CTAs still running, and the next launch starts from local memory.
+    const uint4* src = reinterpret_cast<const uint4*>(p.prefetch_src);
+    uint4* dst = reinterpret_cast<uint4*>(p.prefetch_dst);
+    for (uint32_t i = tid; i < 2 * p.prefetch_n; i += kThreads) {
+      uint4 v;
+      asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+      dst[i] = v;
+    }
   }
 }
 
