@@ -318,3 +318,102 @@ def test_staged_ingest_is_bit_identical():
             nat.check(bus.publish_device_staged(dev.data_ptr() + i * 32, B, (i + B) * 10_000, nxt, B if nxt else 0), "cpbus_publish_device_staged")
         bus.sync()
         tr.compare(bus, orc, n_subs)
+
+
+def _oracle_for_one(gid, mask, codes, srcs, dt_ns=0, timer=None, window=1024):
+    """The exact sequence of ONE subscriber of a huge shard: a 1-subscriber oracle with sub_id_base = gid."""
+    orc = ob.Oracle(1, timers_per_sub=1 if timer else 0, keep_window=window, sub_id_base=gid)
+    orc.subscribe(int(mask))
+    if timer:
+        orc.timer_add(gid, timer[0], timer[1] + gid, False)
+    assert orc.publish_many(codes, srcs, dt_ns=dt_ns) == 0
+    return orc
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full width: 1,048,576 subscribers, one 1 kHz timer each, ticks interleaved.
+    Size-independent checks: every mailbox's count; exact digest + last-1024 window of sampled subscribers
+    against a 1-subscriber oracle placed at that global id; global delivery/tick totals."""
+    import torch
+    n_subs, n_events, B, dt, period = 1_048_576, 1536, 256, 10_000, 1_000_000
+    rng = np.random.default_rng(0xC0DEB203)
+    codes = rng.integers(1, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    ev = np.zeros(n_events, dtype=EVENT_DTYPE)
+    ev["seq"] = np.arange(n_events); ev["ts_ns"] = (np.arange(n_events) + 1) * dt
+    ev["code"], ev["source_id"], ev["target"] = codes, srcs, nat.TARGET_ALL
+    dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32)).cuda()
+    with Bus(n_subs, ring_cap=1024, batch_cap=B, timers_per_sub=1, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+        bus.timer_add_many(0, n_subs, period, source_id0=1_000_000)
+        for i in range(0, n_events, B):
+            nat.check(bus.publish_device(dev.data_ptr() + i * 32, B, (i + B) * dt), "cpbus_publish_device")
+        bus.sync()
+        n_ticks = (n_events * dt) // period
+        d = bus.digests(0, n_subs)
+        assert (d["count"] == n_events + n_ticks).all()
+        for gid in (0, 1, 31, 4097, 65_535, 524_288, 1_048_575):
+            orc = _oracle_for_one(gid, nat.MASK_ALL, codes, srcs, dt_ns=dt, timer=(period, 1_000_000))
+            assert int(d["digest"][gid]) == orc.digest(gid) and int(d["count"][gid]) == orc.count(gid)
+            assert bus.peek_window(gid).tobytes() == orc.mailbox(gid).tobytes()
+        st = bus.stats()
+        assert st["deliveries"] == n_subs * (n_events + n_ticks) and st["ticks"] == n_subs * n_ticks
+        assert len(np.unique(d["digest"])) == n_subs          # tick records carry the owner's id: no two mailboxes alike
+
+
+def test_full_size_config5_properties():
+    """BASELINE config 5 at full width: 1,048,576 Zipf-masked subscribers."""
+    import torch
+    n_subs, n_events, B = 1_048_576, 1024, 256
+    masks = tr.zipf_masks(n_subs, 1.0, 0xC0DEB205); codes = tr.zipf_codes(n_events, 1.0, 0xC0DEB206)
+    srcs = (np.arange(n_events) % 4096).astype(np.uint32)
+    ev = np.zeros(n_events, dtype=EVENT_DTYPE)
+    ev["seq"] = np.arange(n_events); ev["code"], ev["source_id"], ev["target"] = codes, srcs, nat.TARGET_ALL
+    dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32)).cuda()
+    with Bus(n_subs, ring_cap=1024, batch_cap=B, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        bus.subscribe_many(masks)
+        for i in range(0, n_events, B):
+            nat.check(bus.publish_device(dev.data_ptr() + i * 32, B, 0), "cpbus_publish_device")
+        bus.sync()
+        d = bus.digests(0, n_subs)
+        hist = np.bincount(codes, minlength=17).astype(np.uint64)
+        want_counts = np.zeros(n_subs, dtype=np.uint64)
+        for c in range(17):
+            want_counts += ((masks >> np.uint32(c)) & 1).astype(np.uint64) * hist[c]
+        assert (d["count"] == want_counts).all()                # every mailbox's count, closed form
+        for gid in (0, 5, 1023, 77_777, 1_048_575, int(np.argmax(want_counts)), int(np.argmin(want_counts))):
+            orc = _oracle_for_one(gid, masks[gid], codes, srcs)
+            assert int(d["digest"][gid]) == orc.digest(gid)
+            assert bus.peek_window(gid).tobytes() == orc.mailbox(gid).tobytes()
+        # mailboxes with equal masks must agree exactly (no per-subscriber state leaks into the records)
+        order = np.argsort(masks, kind="stable")
+        same = masks[order][1:] == masks[order][:-1]
+        assert (d["digest"][order][1:][same] == d["digest"][order][:-1][same]).all()
+        assert bus.stats()["deliveries"] == int(want_counts.sum())
+
+
+def test_large_clock_jump_is_split_into_bounded_windows():
+    """cpbus_advance over hundreds of timer periods: the host splits it so that no launch sees more than 32/K firings
+    per slot; the mailboxes still match the oracle (which fires them one advance at a time)."""
+    for K, period in ((1, 1000), (4, 700)):
+        orc = ob.Oracle(6, timers_per_sub=K, keep_window=2048)
+        with Bus(6, ring_cap=2048, batch_cap=256, timers_per_sub=K) as bus:
+            for s in range(6):
+                orc.subscribe(); bus.subscribe()
+                orc.timer_add(s, period + 37 * s, 500 + s, False); bus.timer_add(s, period + 37 * s, 500 + s, False)
+            orc.publish(14, 1); nat.check(bus.publish(14, 1), "publish")
+            for now in (999, 250_000, 250_001, 900_000):
+                assert orc.advance(now) == 0; nat.check(bus.advance(now), "advance")
+                orc.publish(5, 2); nat.check(bus.publish(5, 2), "publish")
+            nat.check(bus.flush(), "flush"); bus.sync()
+            st = tr.compare(bus, orc, 6, window=2048)
+            assert st["ticks"] > 1500
+
+
+@pytest.mark.parametrize("seed", range(100, 116))
+def test_random_mixed_traces_more_seeds(seed):
+    K = (0, 1, 2, 4, 8)[seed % 5]
+    ops, n_total = tr.random_ops(seed, 24, 3000, timers_per_sub=K, max_subs=40, p_filter=0.7, p_send=0.05, dt_max=9000)
+    orc = tr.run_oracle(ops, 40, timers_per_sub=K)
+    with Bus(40, ring_cap=4096, batch_cap=(32, 64, 256, 512)[seed % 4], timers_per_sub=K) as bus:
+        tr.run_bus(bus, ops)
+        tr.compare(bus, orc, n_total, window=4096)
