@@ -146,7 +146,12 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     //  1,048,576 subscribers with timers: 8-16 per warp -> 94 %, 4 or 32 per warp 85 %).
     const uint32_t need = (p.n_subs + kWarpsPerCta - 1) / kWarpsPerCta;
     uint32_t spw = b->subs_per_warp;
-    if (!spw) spw = std::max(1u, std::min(16u, (need + (uint32_t)b->sm_count * 7) / (uint32_t)(b->sm_count * 14)));
+    if (!spw) {
+      // ~constant bytes per warp: the counts above were measured at 256-event batches; a 512-event batch halves them
+      const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
+      const uint32_t cap = std::max(1u, 16u / scale);
+      spw = std::max(1u, std::min(cap, (need + (uint32_t)b->sm_count * 7 * scale) / ((uint32_t)b->sm_count * 14 * scale)));
+    }
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
   }
   fanout_kernel<STORE, TIMERS, DIGEST><<<grid, kThreads, smem, b->stream>>>(p);
