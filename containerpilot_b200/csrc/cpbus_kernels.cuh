@@ -22,14 +22,10 @@ namespace cpbus_dev {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-#ifndef CPBUS_TIMERS_MIN_CTAS
-#define CPBUS_TIMERS_MIN_CTAS 4    // timers build: 64 registers, no spills (hot/cold timer slot halves, stats in shared memory)
-#endif
-#ifndef CPBUS_TIMER_PREFETCH
-#define CPBUS_TIMER_PREFETCH 1
-#endif
-#ifndef CPBUS_MIN_CTAS_PER_SM
-#define CPBUS_MIN_CTAS_PER_SM 3   // 80 registers/thread, no spills; 24 resident warps per SM
+// Every variant of the fan-out kernel is held to 64 registers with zero spills => 4 CTAs (32 warps) per SM.
+// Occupancy was the biggest single lever; the macro exists for A/B builds.
+#ifndef CPBUS_CTAS_PER_SM
+#define CPBUS_CTAS_PER_SM 4
 #endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
@@ -144,14 +140,14 @@ __device__ __forceinline__ void st_record(cpbus_event* dst, const uint4& a, cons
   if (STORE == CPBUS_STORE_V8) st_v8(dst, a, b);
   else { st_v4(dst, a); st_v4(reinterpret_cast<unsigned char*>(dst) + 16, b); }
 }
-// 32-byte sector load/store with an L2 eviction-priority hint (control blocks and timer slots are
-// re-read every launch; ring records are write-once streams)
+// 32-byte sector / 16-byte half load/store with an L2 evict_last hint: control blocks and timer slots are
+// re-read every launch, ring records are write-once streams
 __device__ __forceinline__ uint64_t keep_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, uint64_t, bool hinted) {
+__device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, bool hinted) {
   const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
@@ -162,7 +158,7 @@ __device__ __forceinline__ void ld_sector(const void* src, uint4& a, uint4& b, u
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(src));
 }
-__device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4& b, uint64_t, bool hinted) {
+__device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4& b, bool hinted) {
   const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(dst), "r"(a.x), "r"(a.y),
@@ -170,14 +166,14 @@ __device__ __forceinline__ void st_sector(void* dst, const uint4& a, const uint4
                  : "memory");
   else st_v8(dst, a, b);
 }
-__device__ __forceinline__ void ld_half(const void* src, uint4& a, uint64_t, bool hinted) {
+__device__ __forceinline__ void ld_half(const void* src, uint4& a, bool hinted) {
   const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src), "l"(pol));
   else
     asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src));
 }
-__device__ __forceinline__ void st_half(void* dst, const uint4& a, uint64_t, bool hinted) {
+__device__ __forceinline__ void st_half(void* dst, const uint4& a, bool hinted) {
   const uint64_t pol = hinted ? keep_policy() : 0ull;
   if (hinted)
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "l"(pol) : "memory");
@@ -241,7 +237,7 @@ __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
 // TIMERS=false compiles every timer/tick path out (the host knows when no timer is armed): fewer registers,
 // one more resident CTA per SM.
 template <int STORE, bool TIMERS, bool DIGEST>
-__global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPBUS_MIN_CTAS_PER_SM + 1) fanout_kernel(const FanoutParams p) {
+__global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
   cpbus_event* s_batch = reinterpret_cast<cpbus_event*>(smem);
@@ -277,10 +273,10 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
   uint32_t s = blockIdx.x * kWarpsPerCta + warp;
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
   const bool keep = p.hints & 1u;
-  const uint64_t pol_keep = 0;   // the policy is materialised at each use (one instruction) rather than held in registers
+  // (the evict_last policy is materialised at each use — one instruction — rather than held in two registers)
   if (s < p.n_subs) {
-    ld_sector(p.ctl + s, ca, cb, pol_keep, keep);
-    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, pol_keep, keep);
+    ld_sector(p.ctl + s, ca, cb, keep);
+    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
   }
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
@@ -381,8 +377,8 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
     {
       const uint32_t sn = s + wstride;
       if (sn < p.n_subs) {
-        ld_sector(p.ctl + sn, ca, cb, pol_keep, keep);
-        if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)sn * K + tk_slot, ta, pol_keep, keep);
+        ld_sector(p.ctl + sn, ca, cb, keep);
+        if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)sn * K + tk_slot, ta, keep);
       }
     }
     const uint32_t m = cur_b.z;
@@ -478,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       }
       if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
         uint4 cold;
-        ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
+        ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, keep);
         tk_src = cold.x; tk_fired = cold.y;
       }
       if (tk_valid) {
@@ -618,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
       if (n_ticks) {
         if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
           uint4 cold;
-          ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, pol_keep, keep);
+          ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, keep);
           tk_src = cold.x; tk_fired = cold.y;
         }
       }
@@ -643,15 +639,15 @@ __global__ void __launch_bounds__(kThreads, TIMERS ? CPBUS_TIMERS_MIN_CTAS : CPB
         unsigned char* t = reinterpret_cast<unsigned char*>(&p.timers[(size_t)s * K + tk_slot]);
         // this lane has tk_j == 0, so tk_due is the slot's next_due as loaded
         const uint64_t nd = tk_period ? tk_due + (uint64_t)fired_here * tk_period : kTimerIdle;   // one-shot disarms itself
-        st_half(t, make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), (uint32_t)tk_period, (uint32_t)(tk_period >> 32)), pol_keep, keep);
-        st_half(t + 16, make_uint4(tk_src, tk_fired + fired_here, 0u, 0u), pol_keep, keep);
+        st_half(t, make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), (uint32_t)tk_period, (uint32_t)(tk_period >> 32)), keep);
+        st_half(t + 16, make_uint4(tk_src, tk_fired + fired_here, 0u, 0u), keep);
       }
     }
     if (lane == 0 && k) {   // one full-sector write of the control block
       const uint64_t nt = tail + k;
       const uint64_t nd = DIGEST ? dig * s_pow[k] + dsum : dig;
       st_sector(p.ctl + s, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), cur_a.z, cur_a.w),   // head: consumer-owned, passed through
-                make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u), pol_keep, keep);
+                make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), m, 0u), keep);
       atomicAdd(&s_sum->acc_deliv, k);
       if (DIGEST) {
         const uint32_t f = (uint32_t)nd ^ (uint32_t)(nd >> 32);
