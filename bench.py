@@ -183,7 +183,9 @@ def main():
     K_timers = 1 if wl["timers"] else 0
 
     # ---- synthetic trace, resident in HBM (rank 0 is the publisher's GPU) ----
-    n_trace_batches = min(steps + warmup, 16384)       # cycled; 16384 x 8 KiB = 128 MiB
+    # trace length: long enough that the timed region of a short run never crosses a re-stamp boundary, and the default
+    # full run crosses at most one (32768 batches x 16 KiB = 512 MiB of HBM)
+    n_trace_batches = min(max(steps + warmup, 2048), 32768)
     n_ev = n_trace_batches * B
     g = torch.Generator(device="cpu"); g.manual_seed(0xC0DEB200 + 2)
     if wl["zipf"]:
@@ -301,6 +303,19 @@ def main():
     settle, t_settle = 0, time.perf_counter()
     while time.perf_counter() - t_settle < 0.3 and settle < 20_000:
         run_steps(100); torch.cuda.synchronize(); settle += 100
+    # if the timed region would straddle the end of the trace, start it at the next cycle instead (re-stamp outside the timing)
+    pos = state["step"] % n_trace_batches
+    if steps <= n_trace_batches and pos + steps > n_trace_batches:
+        cycle = state["step"] // n_trace_batches + 1
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        restamp(cycle)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        state["step"] = cycle * n_trace_batches
+        nat.check(bus.advance(state["step"] * B * DT_NS), "cpbus_advance")   # armed timers catch up in bounded windows
     barrier()
     st0 = bus.stats()
     sampler.samples.clear(); sampler.reasons.clear()
@@ -309,6 +324,7 @@ def main():
     e0.record(stream)
     run_steps(steps, trace_chunks=bool(os.environ.get("CPBUS_BENCH_TRACE")))
     e1.record(stream)
+    sampler.sample()                                                   # launches are asynchronous: the GPU is still inside the timed region here
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
