@@ -146,6 +146,15 @@ class Bus:
         nat.check(self._lib.cpbus_drain(self._h, sub_id, out.ctypes.data, cap, C.byref(n), C.byref(lost)), "cpbus_drain")
         return out[: n.value]
 
+    def drain_many(self, first_sub: int, n: int, cap: int):
+        """Bulk drain: returns (records, offsets, counts); mailbox i's FIFO run is records[offsets[i]:offsets[i]+counts[i]]."""
+        out = np.zeros(cap, dtype=EVENT_DTYPE)
+        offs, cnts = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        total = C.c_size_t()
+        nat.check(self._lib.cpbus_drain_many(self._h, first_sub, n, out.ctypes.data, cap, offs.ctypes.data, cnts.ctypes.data,
+                                             C.byref(total)), "cpbus_drain_many")
+        return out, offs, cnts
+
     def peek_window(self, sub_id: int, cap: int | None = None) -> np.ndarray:
         cap = cap or self.ring_cap
         out = np.zeros(cap, dtype=EVENT_DTYPE)

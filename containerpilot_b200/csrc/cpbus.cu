@@ -61,6 +61,8 @@ struct cpbus {
   size_t prefetched_n = 0;
   int prefetch_cur = 0;
   std::vector<void*> shared_owned, shared_mapped;   // cpbus_shared_alloc / cpbus_shared_open
+  cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
+  uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
@@ -86,7 +88,6 @@ struct cpbus {
   // registry mirror (events/bus.go:13 `registry map[*Subscriber]bool`)
   std::vector<uint32_t> h_mask;
   std::vector<uint8_t> h_active;
-  std::vector<uint64_t> h_drained;        // consumer cursor as the host last left it (to report overwritten records)
   std::vector<size_t> oneshot_idx;        // armed one-shot timers (index into h_timers)
   std::vector<HostTimer> h_timers;        // N*K, allocated on first timer
   uint32_t n_next = 0, n_active = 0, n_timers = 0;
@@ -402,7 +403,6 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   }
   b->h_mask.assign(N, 0);
   b->h_active.assign(N, 0);
-  b->h_drained.assign(N, 0);
   b->intern.emplace(std::string(), 0u);   // "" -> 0 so that NonEvent == {None, 0} (events/events.go:45)
   b->sources.emplace_back();
   *out = b;
@@ -423,6 +423,7 @@ int cpbus_destroy(cpbus_t* b) {
     if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  cudaFree(b->d_drain); cudaFree(b->d_drain_idx);
   cudaFree(b->d_result); cudaFree(b->d_batch_local); cudaFree(b->d_prefetch[0]); cudaFree(b->d_prefetch[1]);
   for (void* p : b->shared_mapped) cudaIpcCloseMemHandle(p);
   for (void* p : b->shared_owned) cudaFree(p);
@@ -718,13 +719,14 @@ int cpbus_shared_close(cpbus_t* b, void* dptr) {
   return CPBUS_ENOENT;
 }
 
-static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head) {
+static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head, uint64_t* lost = nullptr) {
   SubCtl c{};
   CK(cudaMemcpyAsync(&c, b->d_ctl + l, sizeof(SubCtl), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *tail = c.tail;
   // overwrite-oldest: the consumer's cursor can never be older than the oldest record still in the ring
   *head = (!b->lossless && c.tail > b->R && c.tail - b->R > c.head) ? c.tail - b->R : c.head;
+  if (lost) *lost = *head - c.head;   // records overwritten since the consumer's stored cursor
   return CPBUS_OK;
 }
 
@@ -745,15 +747,49 @@ int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
   uint64_t tail = 0, head = 0;
-  if ((rc = read_cursors(b, l, &tail, &head))) return rc;
-  if (lost) { *lost = head - b->h_drained[l]; }
+  uint64_t gone = 0;
+  if ((rc = read_cursors(b, l, &tail, &head, &gone))) return rc;
+  if (lost) *lost = gone;
   const size_t take = (size_t)std::min<uint64_t>(tail - head, cap);
   if (take && (rc = copy_slots(b, l, head, take, out))) return rc;
   head += take;
-  b->h_drained[l] = head;
   CK(cudaMemcpyAsync(&b->d_ctl[l].head, &head, 8, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *n = take;
+  return CPBUS_OK;
+}
+
+// Bulk drain: everything undrained in mailboxes [first_sub, first_sub+n) in ONE kernel + two D2H copies.
+// out receives the records (each mailbox's run contiguous and FIFO), offsets[i]/counts[i] say where mailbox i's run is.
+int cpbus_drain_many(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_event* out, size_t cap, uint32_t* offsets,
+                     uint32_t* counts, size_t* total) {
+  if (!b || !n || !out || !cap || !offsets || !counts || !total || cap > 0xFFFFFFFFull) return CPBUS_EINVAL;
+  const uint32_t l = first_sub - b->cfg.sub_id_base;
+  if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  if (b->drain_cap < cap || b->drain_idx_cap < n) {   // device staging grows on demand and is kept
+    if (b->drain_cap < cap) { cudaFree(b->d_drain); b->d_drain = nullptr; CK(cudaMalloc((void**)&b->d_drain, cap * sizeof(cpbus_event))); b->drain_cap = cap; }
+    if (b->drain_idx_cap < n) { cudaFree(b->d_drain_idx); b->d_drain_idx = nullptr; CK(cudaMalloc((void**)&b->d_drain_idx, (size_t)n * sizeof(uint2) + 16)); b->drain_idx_cap = n; }
+  }
+  unsigned int* cursor = reinterpret_cast<unsigned int*>(b->d_drain_idx + n);
+  CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned int), b->stream));
+  const uint32_t threads = 256, grid = std::min<uint32_t>((n + 7) / 8, (uint32_t)b->sm_count * 8);
+  drain_many_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, b->d_ring, l, n, b->R, b->lossless ? 1u : 0u, b->d_drain,
+                                                     (uint32_t)cap, b->d_drain_idx, cursor);
+  CK(cudaGetLastError());
+  b->st.kernel_launches++;
+  std::vector<uint2> idx(n);
+  CK(cudaMemcpyAsync(idx.data(), b->d_drain_idx, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  size_t tot = 0, hi = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    offsets[i] = idx[i].x; counts[i] = idx[i].y; tot += idx[i].y;
+    hi = std::max<size_t>(hi, (size_t)idx[i].x + idx[i].y);
+  }
+  if (hi) CK(cudaMemcpyAsync(out, b->d_drain, hi * sizeof(cpbus_event), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  *total = tot;
   return CPBUS_OK;
 }
 

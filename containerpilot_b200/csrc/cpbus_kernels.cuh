@@ -733,6 +733,38 @@ __global__ void overwritten_kernel(const SubCtl* ctl, uint32_t n, uint32_t ring_
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// Bulk drain (the mailbox -> `chan Event` bridge for many subscribers at once): one warp per mailbox claims space in a
+// contiguous staging buffer with a single atomic, copies its undrained records there in FIFO order and advances the
+// consumer cursor.  index[s] = {offset in records, count}; a mailbox that does not fit entirely is left for the next call.
+__global__ void drain_many_kernel(SubCtl* ctl, const cpbus_event* ring, uint32_t first, uint32_t n, uint32_t ring_cap,
+                                  uint32_t lossless, cpbus_event* out, uint32_t out_cap, uint2* index, unsigned int* cursor) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = w; i < n; i += nw) {
+    SubCtl* c = ctl + first + i;
+    const unsigned long long tail = c->tail;
+    unsigned long long head = c->head;
+    if (!lossless && tail > ring_cap && tail - ring_cap > head) head = tail - ring_cap;   // overwritten before being taken
+    const uint32_t avail = (uint32_t)(tail - head);
+    uint32_t off = 0;
+    if (lane == 0 && avail) off = atomicAdd(cursor, avail);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    const bool fits = avail && off + avail <= out_cap;
+    if (fits) {
+      const cpbus_event* r = ring + (size_t)(first + i) * ring_cap;
+      for (uint32_t j = lane; j < avail; j += 32) {
+        const uint4* src = reinterpret_cast<const uint4*>(r + ((head + j) & (ring_cap - 1)));
+        uint4* dst = reinterpret_cast<uint4*>(out + off + j);
+        dst[0] = src[0]; dst[1] = src[1];
+      }
+    }
+    if (lane == 0) {
+      index[i] = make_uint2(fits ? off : 0u, fits ? avail : 0u);
+      if (fits) c->head = tail;
+    }
+  }
+}
+
 // (count, digest) folds over a range of mailboxes: one 32-byte result instead of 16 B per subscriber
 __global__ void digest_fold_kernel(const SubCtl* ctl, uint32_t first, uint32_t n, uint32_t sub_base,
                                    unsigned long long* out4) {

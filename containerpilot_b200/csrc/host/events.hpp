@@ -11,6 +11,7 @@
 // installed in this image, so the compiled-language mirror is C++17.  Go panics are `events::Panic`.
 // Every delivery goes through libcpbus (CUDA): mailboxes live in HBM and a pump moves them into `Rx`.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -312,7 +313,35 @@ class EventBus {   // events/bus.go:12-22
       sub->pending_.pop_front();
     }
   }
-  void DrainAll(bool blocking) { for (auto& kv : registry_) DrainOne(kv.first, blocking); }
+  // All mailboxes at once: one gather kernel + two D2H copies (cpbus_drain_many) instead of a round trip per subscriber.
+  void DrainAll(bool blocking) {
+    if (registry_.empty()) return;
+    uint32_t lo = UINT32_MAX, hi = 0;
+    for (auto& kv : registry_) { lo = std::min(lo, kv.second); hi = std::max(hi, kv.second); }
+    const uint32_t n = hi - lo + 1;
+    if (drain_buf_.size() < kDrainCap) drain_buf_.resize(kDrainCap);
+    drain_off_.resize(n); drain_cnt_.resize(n);
+    std::vector<Subscriber*> by_id(n, nullptr);
+    for (auto& kv : registry_) by_id[kv.second - lo] = kv.first;
+    for (;;) {
+      size_t total = 0;
+      Check(cpbus_drain_many(h_, lo, n, drain_buf_.data(), kDrainCap, drain_off_.data(), drain_cnt_.data(), &total), "cpbus_drain_many");
+      if (!total) break;
+      for (uint32_t i = 0; i < n; i++) {
+        if (!drain_cnt_[i] || !by_id[i]) continue;
+        const cpbus_event* r = drain_buf_.data() + drain_off_[i];
+        for (uint32_t j = 0; j < drain_cnt_[i]; j++) by_id[i]->pending_.push_back(Event{(EventCode)r[j].code, Source(r[j].source_id)});
+      }
+    }
+    for (auto& kv : registry_) {
+      Subscriber* sub = kv.first;
+      while (!sub->pending_.empty() && sub->Rx) {
+        if (blocking) sub->Rx->Send(sub->pending_.front());
+        else if (!sub->Rx->TrySend(sub->pending_.front())) break;
+        sub->pending_.pop_front();
+      }
+    }
+  }
   void PumpLoop() {
     while (!stop_) {
       std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -325,6 +354,9 @@ class EventBus {   // events/bus.go:12-22
     }
   }
 
+  static constexpr size_t kDrainCap = 1 << 16;
+  std::vector<cpbus_event> drain_buf_;
+  std::vector<uint32_t> drain_off_, drain_cnt_;
   cpbus_t* h_ = nullptr;
   std::recursive_mutex lock_;   // bus.lock (bus.go:14): serialises publishers and membership changes
   bool reload_ = false;

@@ -189,6 +189,12 @@ int cpbus_shared_close(cpbus_t* bus, void* dptr);
 /* Mailbox -> host, FIFO (`<-sub.Rx`).  *lost = records overwritten before they
  * could be drained (always 0 in lossless mode). */
 int cpbus_drain(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n, uint64_t* lost);
+/* Bulk drain of mailboxes [first_sub, first_sub+n): one kernel gathers every undrained record into a staging
+ * buffer (one atomic per mailbox), two D2H copies bring them back.  out[offsets[i] .. offsets[i]+counts[i]) is mailbox
+ * i's run, FIFO.  A mailbox whose run does not fit into `cap` is left untouched (counts[i] = 0) for the next call;
+ * *total = records returned.  This is what the `chan Event` pump of a shim with many subscribers calls. */
+int cpbus_drain_many(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_event* out, size_t cap,
+                     uint32_t* offsets, uint32_t* counts, size_t* total);
 /* Last min(cap, ring_cap, count) delivered records, oldest first, without consuming. */
 int cpbus_peek_window(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n);
 int cpbus_digest(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_digest_t* out);

@@ -417,3 +417,35 @@ def test_random_mixed_traces_more_seeds(seed):
     with Bus(40, ring_cap=4096, batch_cap=(32, 64, 256, 512)[seed % 4], timers_per_sub=K) as bus:
         tr.run_bus(bus, ops)
         tr.compare(bus, orc, n_total, window=4096)
+
+
+def test_drain_many_bulk_bridge():
+    """cpbus_drain_many: one kernel + two copies drain thousands of mailboxes; per-mailbox runs are FIFO and complete,
+    a mailbox that does not fit stays for the next call, and draining twice returns nothing new."""
+    n_subs = 3000
+    rng = np.random.default_rng(77)
+    masks = np.where(rng.random(n_subs) < 0.5, nat.MASK_ALL, rng.integers(0, 1 << 17, n_subs)).astype(np.uint32)
+    orc = ob.Oracle(n_subs)
+    with Bus(n_subs, ring_cap=256, batch_cap=128, lossless=True) as bus:
+        bus.subscribe_many(masks)
+        for m in masks:
+            orc.subscribe(int(m))
+        got = [[] for _ in range(n_subs)]
+        for rnd in range(5):
+            codes = rng.integers(0, 17, 100).astype(np.uint32); srcs = rng.integers(0, 30, 100).astype(np.uint32)
+            orc.publish_many(codes, srcs)
+            for c, s_ in zip(codes, srcs):
+                nat.check(bus.publish(int(c), int(s_)), "publish")
+            nat.check(bus.flush(), "flush")
+            cap = 40_000 if rnd % 2 == 0 else 400_000        # the small capacity forces some mailboxes to wait for the next call
+            for _ in range(40):
+                recs, offs, cnts = bus.drain_many(0, n_subs, cap)
+                if cnts.sum() == 0:
+                    break
+                for s in np.nonzero(cnts)[0]:
+                    got[s].append(recs[offs[s]: offs[s] + cnts[s]].copy())
+        for s in range(n_subs):
+            seq = np.concatenate(got[s]) if got[s] else np.zeros(0, dtype=EVENT_DTYPE)
+            assert seq.tobytes() == orc.mailbox(s).tobytes(), f"subscriber {s}"
+        recs, offs, cnts = bus.drain_many(0, n_subs, 1000)
+        assert cnts.sum() == 0 and bus.stats()["overwritten"] == 0
