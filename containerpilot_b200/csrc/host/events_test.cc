@@ -212,6 +212,26 @@ static void TestConfig1Plumbing() {
   EXPECT(bus.Wait() == false);
 }
 
+// many subscribers through the bulk drain bridge (cpbus_drain_many): 300 mailboxes, 600 events, virtual clock
+static void TestManySubscribers() {
+  std::printf("TestManySubscribers\n");
+  EventBus bus(EventBus::Clock::Virtual, 512);
+  const int N = 300, E = 600;
+  std::vector<std::unique_ptr<Subscriber>> subs;
+  for (int i = 0; i < N; i++) { subs.emplace_back(new Subscriber()); subs.back()->Rx = MakeChan(1000); subs.back()->Subscribe(&bus); }
+  std::vector<Event> sent;
+  for (int i = 0; i < E; i++) { Event e{(EventCode)(1 + i % 16), "s" + std::to_string(i % 37)}; sent.push_back(e); bus.Publish(e); }
+  bool ok = true;
+  for (auto& s : subs) {
+    std::vector<Event> got; Event e;
+    while (s->Rx->Recv(&e)) got.push_back(e);
+    ok = ok && got == sent;
+  }
+  EXPECT(ok);
+  for (auto& s : subs) s->Unsubscribe();
+  EXPECT(bus.Wait() == false);
+}
+
 int main() {
   TestNames();
   TestPubSubInterfaces();
@@ -221,6 +241,7 @@ int main() {
   TestPanics();
   TestTimers();
   TestConfig1Plumbing();
+  TestManySubscribers();
   std::printf(failures ? "FAILED (%d)\n" : "PASS\n", failures);
   return failures ? 1 : 0;
 }
