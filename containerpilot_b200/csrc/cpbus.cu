@@ -64,6 +64,7 @@ struct cpbus {
   cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
+  bool pdl = true;                        // programmatic dependent launch of consecutive fan-outs
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
   unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
@@ -155,7 +156,13 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
     }
     grid = std::max(1u, std::min((need + spw - 1) / spw, need));
   }
-  fanout_kernel<STORE, TIMERS, DIGEST><<<grid, kThreads, smem, b->stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = b->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the next fan-out's prologue overlaps this one's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = b->pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, fanout_kernel<STORE, TIMERS, DIGEST>, p));
   CK(cudaGetLastError());
   return CPBUS_OK;
 }
@@ -166,11 +173,14 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
-  p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.desc = b->d_desc; p.desc_ready = b->d_desc_ready; p.launch_seq = ++b->launch_seq; p.w_now = w;
+  p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.launch_seq = ++b->launch_seq;
+  p.desc = b->d_desc + (p.launch_seq & 1) * fanout_desc_bytes(2048);   // two descriptor buffers: launch i+1 may write while launch i reads
+  p.desc_ready = b->d_desc_ready + (p.launch_seq & 1) * 16; p.w_now = w;
   p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
   p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
   p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u;
-  p.prefetch_src = prefetch_src; p.prefetch_dst = prefetch_dst; p.prefetch_n = prefetch_n; p.n_ev = n;
+  p.prefetch_src = prefetch_src; p.prefetch_dst = prefetch_dst; p.prefetch_n = prefetch_n;
+  p.batch_dep = (d_src == b->d_prefetch[0] || d_src == b->d_prefetch[1]) ? 1u : 0u; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
@@ -342,6 +352,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  if (const char* e = getenv("CPBUS_PDL")) b->pdl = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);
   if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
   int rc = CPBUS_OK;
@@ -367,8 +378,8 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_ctl, N * sizeof(SubCtl));
   if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
   ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32 * cpbus::kFoldSlots); ALLOC(b->d_pow, kPowTableLen * 8);
-  ALLOC(b->d_desc, fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 128);
-  if (cudaMemsetAsync(b->d_desc_ready, 0, 128, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
+  ALLOC(b->d_desc, 2 * fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 256);
+  if (cudaMemsetAsync(b->d_desc_ready, 0, 256, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
   for (int i = 0; i < cpbus::kStage; i++) {
     ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));

@@ -85,6 +85,7 @@ struct FanoutParams {
   const cpbus_event* prefetch_src;   // next batch in the publisher GPU's HBM (peer pointer) or nullptr
   cpbus_event* prefetch_dst;         // local buffer it is pulled into while this launch's stores are in flight
   uint32_t prefetch_n;
+  uint32_t batch_dep;         // 1: `batch` was produced by the previous launch (prefetch buffer): wait for it before staging
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -252,6 +253,10 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const uint32_t n = p.n_ev;
 
   // ---- stage the batch: one elected thread drives the TMA engine ----
+  // Programmatic dependent launch: this kernel may begin while the previous fan-out is still draining its last wave.
+  // Everything up to `griddepcontrol.wait` touches only data that the previous launch never writes (the batch, the
+  // power table, this launch's descriptor buffer); mailboxes, control blocks and timers come after it.
+  if (p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid == 0) { mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0; }
   __syncthreads();
   if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
@@ -264,20 +269,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     bulk_g2s(s_pow, p.pow_table, pow_bytes, &s_sum->mbar);
   }
 
-  // software pipeline, stage 0: the first subscriber's control block (and timer slot) is requested
-  // before anything else so that its DRAM round trip overlaps the staging below
-  const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
-  const uint32_t tk_slot = lane / J, tk_j = lane % J;
-  const bool timers_on = TIMERS && p.timers_on && K;
-  const uint32_t wstride = gridDim.x * kWarpsPerCta;
-  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
-  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
   const bool keep = p.hints & 1u;
   // (the evict_last policy is materialised at each use — one instruction — rather than held in two registers)
-  if (s < p.n_subs) {
-    ld_sector(p.ctl + s, ca, cb, keep);
-    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
-  }
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
   // descriptor = [rhash | meta | Q] (24*cap + 16 bytes, same layout as shared memory) + {present, has_unicast, hist[32]}
@@ -362,6 +355,20 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     mbar_wait(&s_sum->mbar, (p.staged && n) ? 1u : 0u);
     __syncthreads();
   }
+  const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
+  const uint32_t tk_slot = lane / J, tk_j = lane % J;
+  const bool timers_on = TIMERS && p.timers_on && K;
+  const uint32_t wstride = gridDim.x * kWarpsPerCta;
+  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+  // ---- from here on the previous launch's results are needed: wait for it, then let the NEXT launch start its prologue
+  // (the trigger comes after the wait so that a launch can never overlap its grand-parent: two descriptor buffers suffice)
+  if (!p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+  uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
+  if (s < p.n_subs) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
+    ld_sector(p.ctl + s, ca, cb, keep);
+    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
+  }
   const uint32_t present = s_sum->present;
   const bool has_unicast = s_sum->has_unicast != 0;
   const uint32_t Rm = p.ring_cap - 1;
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         // order simultaneous firings by (due, slot): rank = #valid ticks with a smaller key
         if (J == 32 || (tk_mask >> J) == 0) tk_rank = tk_j;       // only slot 0 fired
         else {
+#pragma unroll 1
           for (int t = 0; t < 32; t++) {
             if (!((tk_mask >> t) & 1u)) continue;      // warp-uniform
             const uint64_t od = shfl64(tk_due, t);
@@ -462,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       // event i lands at i + #{ticks with pos <= i}.  Tick positions are sorted, so the count is warp-uniform for a
       // whole 32-event chunk unless a tick falls strictly inside it (rare: 2-3 ticks per 256 events in config 3).
       uint32_t t_idx = 0;
+#pragma unroll 1
       for (uint32_t c0 = 0; c0 < n; c0 += 32) {
         while (t_idx < n_ticks && my_tick[t_idx] <= c0) t_idx++;
         const uint32_t i = c0 + lane;
