@@ -283,8 +283,8 @@ def main():
                 dist.broadcast(trace_dev[slot * B: hi * B], src=0)
             wm = (i + 1) * B * DT_NS
             if fused:
-                nslot = (slot + 1) % n_trace_batches                   # next batch: pulled by THIS launch, hidden under its stores
-                nxt_ptr = src_ptr + nslot * B * 32 if nslot else 0     # (not across a re-stamp boundary)
+                nslot = slot + 2                                       # the batch after next: pulled by THIS launch, hidden under its stores
+                nxt_ptr = src_ptr + nslot * B * 32 if nslot < n_trace_batches else 0   # (not across a re-stamp boundary)
                 nat.check(bus.publish_device_staged(src_ptr + slot * B * 32, B, wm, nxt_ptr, B if nxt_ptr else 0), "cpbus_publish_device_staged")
             else:
                 nat.check(bus.publish_device(src_ptr + slot * B * 32, B, wm), "cpbus_publish_device")

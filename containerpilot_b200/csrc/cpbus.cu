@@ -56,10 +56,12 @@ struct cpbus {
   unsigned long long* d_desc_ready = nullptr;
   unsigned long long launch_seq = 0;
   cpbus_event* d_batch_local = nullptr;    // staged ingest: CTA 0's local copy of a peer batch
-  cpbus_event* d_prefetch[2] = {nullptr, nullptr};   // fused ingest: next batch, pulled by the previous launch
-  const void* prefetched_ptr = nullptr;    // which peer batch sits in d_prefetch[prefetch_cur]
-  size_t prefetched_n = 0;
-  int prefetch_cur = 0;
+  static constexpr int kPrefetch = 3;      // fused ingest: later batches pulled over NVLink by earlier launches
+  cpbus_event* d_prefetch[kPrefetch] = {};
+  const void* pf_ptr[kPrefetch] = {};      // which peer batch sits in d_prefetch[i] ...
+  size_t pf_n[kPrefetch] = {};
+  unsigned long long pf_seq[kPrefetch] = {};   // ... and which launch wrote it
+  int pf_next = 0;
   std::vector<void*> shared_owned, shared_mapped;   // cpbus_shared_alloc / cpbus_shared_open
   cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
@@ -169,7 +171,8 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
 
 // fan out `n` records at d_src with watermark w (all checks done by the caller)
 int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool staged = false,
-                  const cpbus_event* prefetch_src = nullptr, cpbus_event* prefetch_dst = nullptr, uint32_t prefetch_n = 0) {
+                  const cpbus_event* prefetch_src = nullptr, cpbus_event* prefetch_dst = nullptr, uint32_t prefetch_n = 0,
+                  bool batch_dep = false) {
   if (b->n_next == 0) return CPBUS_OK;
   if (n == 0 && b->n_timers == 0) return CPBUS_OK;
   FanoutParams p{};
@@ -180,7 +183,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
   p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u;
   p.prefetch_src = prefetch_src; p.prefetch_dst = prefetch_dst; p.prefetch_n = prefetch_n;
-  p.batch_dep = (d_src == b->d_prefetch[0] || d_src == b->d_prefetch[1]) ? 1u : 0u; p.n_ev = n;
+  p.batch_dep = batch_dep ? 1u : 0u; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
@@ -388,7 +391,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   }
   ALLOC(b->d_batch_local, (size_t)B * sizeof(cpbus_event));
-  ALLOC(b->d_prefetch[0], (size_t)B * sizeof(cpbus_event)); ALLOC(b->d_prefetch[1], (size_t)B * sizeof(cpbus_event));
+  for (int i = 0; i < cpbus::kPrefetch; i++) ALLOC(b->d_prefetch[i], (size_t)B * sizeof(cpbus_event));
   ALLOC(b->d_result, sizeof(DevResultSlot) * kResultRing * kResultSub);
   if (cudaMemsetAsync(b->d_result, 0, sizeof(DevResultSlot) * kResultRing * kResultSub, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaMallocHost((void**)&b->h_result, sizeof(DevResultSlot) * 8 * kResultSub) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -435,7 +438,8 @@ int cpbus_destroy(cpbus_t* b) {
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   cudaFree(b->d_drain); cudaFree(b->d_drain_idx);
-  cudaFree(b->d_result); cudaFree(b->d_batch_local); cudaFree(b->d_prefetch[0]); cudaFree(b->d_prefetch[1]);
+  cudaFree(b->d_result); cudaFree(b->d_batch_local);
+  for (int i = 0; i < cpbus::kPrefetch; i++) cudaFree(b->d_prefetch[i]);
   for (void* p : b->shared_mapped) cudaIpcCloseMemHandle(p);
   for (void* p : b->shared_owned) cudaFree(p);
   if (b->h_result) cudaFreeHost(b->h_result);
@@ -666,15 +670,25 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
   if (!ok) return CPBUS_EAGAIN;
   b->now = watermark_ns;
   const cpbus_event* src = (const cpbus_event*)d_events;
-  if (staged && n && b->prefetched_ptr == d_events && b->prefetched_n == n) {
-    src = b->d_prefetch[b->prefetch_cur];   // the previous launch already pulled this batch over NVLink: plain local launch
-    staged = false;
+  bool dep = false;
+  if (staged && n) {
+    for (int i = 0; i < cpbus::kPrefetch; i++)
+      if (b->pf_ptr[i] == d_events && b->pf_n[i] == n) {
+        src = b->d_prefetch[i];          // an earlier launch already pulled this batch over NVLink: plain local launch
+        staged = false;
+        dep = b->pf_seq[i] == b->launch_seq;   // written by the IMMEDIATELY preceding launch: its prologue must not run ahead
+        break;
+      }
   }
   const cpbus_event* pf_src = nullptr; cpbus_event* pf_dst = nullptr;
-  if (d_next && n_next) { pf_src = (const cpbus_event*)d_next; pf_dst = b->d_prefetch[b->prefetch_cur ^ 1]; }
-  if ((rc = launch_fanout(b, src, (uint32_t)n, watermark_ns, staged, pf_src, pf_dst, (uint32_t)n_next))) return rc;
-  if (pf_src) { b->prefetch_cur ^= 1; b->prefetched_ptr = d_next; b->prefetched_n = n_next; }
-  else { b->prefetched_ptr = nullptr; b->prefetched_n = 0; }
+  int slot = -1;
+  if (d_next && n_next) {
+    slot = b->pf_next;
+    if (b->d_prefetch[slot] == src) slot = (slot + 1) % cpbus::kPrefetch;   // never overwrite the buffer this launch reads
+    pf_src = (const cpbus_event*)d_next; pf_dst = b->d_prefetch[slot];
+  }
+  if ((rc = launch_fanout(b, src, (uint32_t)n, watermark_ns, staged, pf_src, pf_dst, (uint32_t)n_next, dep))) return rc;
+  if (slot >= 0) { b->pf_ptr[slot] = d_next; b->pf_n[slot] = n_next; b->pf_seq[slot] = b->launch_seq; b->pf_next = (slot + 1) % cpbus::kPrefetch; }
   b->st.publishes += n; b->seq += n;
   return CPBUS_OK;
 }

@@ -170,9 +170,10 @@ int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t 
 /* Same, but d_events may point into ANOTHER GPU's HBM (the publisher's event stream, peer-mapped over
  * NVLink, e.g. through CUDA IPC): one CTA of the fan-out kernel pulls the batch across the link, stages it
  * locally and hands it to the other CTAs together with the batch descriptor — the broadcast of SURVEY.md §8e
- * fused into the fan-out launch, no collective call.  If d_next/n_next name the FOLLOWING batch, the same launch
- * also pulls it (the NVLink transfer hides under this launch's stores) and the next call, given that pointer as its
- * d_events, starts from local memory.  The caller guarantees the peer batches are complete and stable while the
+ * fused into the fan-out launch, no collective call.  If d_next/n_next name a LATER batch (the next one, or better
+ * the one after it), the same launch also pulls that batch (the NVLink transfer hides under this launch's stores) and
+ * a later call given that pointer as its d_events starts from local memory; a batch pulled two launches earlier also
+ * lets that launch's prologue overlap its predecessor (programmatic dependent launch).  The caller guarantees the peer batches are complete and stable while the
  * launch runs (throughput mode only). */
 int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns,
                                 const void* d_next, size_t n_next);

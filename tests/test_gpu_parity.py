@@ -314,7 +314,8 @@ def test_staged_ingest_is_bit_identical():
         bus.timer_add_many(0, n_subs, 333_000, source_id0=7000)
         for i in range(0, n_events, B):
             # every other call names the next batch so that both the pull-now and the prefetched paths are exercised
-            nxt = dev.data_ptr() + (i + B) * 32 if (i // B) % 3 != 2 and i + B < n_events else 0
+            d = (1, 2, 2, 1, 0)[(i // B) % 5]                       # hint the next batch, the one after it, or nothing
+            nxt = dev.data_ptr() + (i + d * B) * 32 if d and i + d * B < n_events else 0
             nat.check(bus.publish_device_staged(dev.data_ptr() + i * 32, B, (i + B) * 10_000, nxt, B if nxt else 0), "cpbus_publish_device_staged")
         bus.sync()
         tr.compare(bus, orc, n_subs)
