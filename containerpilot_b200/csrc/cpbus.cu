@@ -67,6 +67,8 @@ struct cpbus {
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
   bool pdl = true;                        // programmatic dependent launch of consecutive fan-outs
+  bool zero_copy = false;                 // fan-out pulls host-staged batches straight from pinned memory (experiment: CPBUS_ZERO_COPY=1)
+  cudaEvent_t launched = nullptr;         // recorded after the latest fan-out (step results are read on the copy stream)
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
   static constexpr int kFoldSlots = 8;
   unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
@@ -249,6 +251,18 @@ int flush_staged(cpbus* b, uint64_t w) {
   const uint32_t n = (uint32_t)b->n_staged;
   if (n == 0 && (b->n_timers == 0 || w == b->last_watermark)) return CPBUS_OK;
   const int c = b->cur;
+  int rc;
+  if (b->zero_copy && !b->lossless) {
+    // Zero-copy ingest: the pinned staging buffer is mapped into the device address space; CTA 0 of the fan-out pulls the
+    // batch over PCIe in its prologue (the staged path) — no H2D op, no stream waits, consecutive fan-outs stay adjacent.
+    rc = launch_fanout(b, b->h_batch[c], n, w, /*staged=*/true);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->consumed[c], b->stream));
+    b->n_staged = 0;
+    b->cur = (b->cur + 1) % cpbus::kStage;
+    CK(cudaEventSynchronize(b->consumed[b->cur]));   // the launch that read the buffer we are about to overwrite has finished
+    return CPBUS_OK;
+  }
   if (n) {
     CK(cudaStreamWaitEvent(b->copy_stream, b->consumed[c], 0));   // the previous user of d_batch[c] is done
     CK(cudaMemcpyAsync(b->d_batch[c], b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->copy_stream));
@@ -256,7 +270,7 @@ int flush_staged(cpbus* b, uint64_t w) {
     CK(cudaStreamWaitEvent(b->stream, b->h2d_done[c], 0));
   }
   bool ok = true;
-  int rc = admit(b, b->d_batch[c], n, w, &ok);
+  rc = admit(b, b->d_batch[c], n, w, &ok);
   if (rc) return rc;
   if (!ok) return CPBUS_EAGAIN;   // staged events stay staged; drain and call flush again
   rc = launch_fanout(b, b->d_batch[c], n, w);
@@ -356,6 +370,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
   if (const char* e = getenv("CPBUS_PDL")) b->pdl = atoi(e) != 0;
+  if (const char* e = getenv("CPBUS_ZERO_COPY")) b->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);
   if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
   int rc = CPBUS_OK;
@@ -384,6 +399,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_desc, 2 * fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 256);
   if (cudaMemsetAsync(b->d_desc_ready, 0, 256, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (cudaEventCreateWithFlags(&b->launched, cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   for (int i = 0; i < cpbus::kStage; i++) {
     ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));
     if (cudaMallocHost((void**)&b->h_batch[i], (size_t)B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
@@ -437,6 +453,7 @@ int cpbus_destroy(cpbus_t* b) {
     if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  if (b->launched) cudaEventDestroy(b->launched);
   cudaFree(b->d_drain); cudaFree(b->d_drain_idx);
   cudaFree(b->d_result); cudaFree(b->d_batch_local);
   for (int i = 0; i < cpbus::kPrefetch; i++) cudaFree(b->d_prefetch[i]);
@@ -886,8 +903,11 @@ int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) {
   int rc = dev_guard(b); if (rc) return rc;
   const uint32_t t = b->result_next++ % 8;
   const DevResultSlot* src = b->d_result + (size_t)(b->launch_seq % kResultRing) * kResultSub;
-  CK(cudaMemcpyAsync(b->h_result + (size_t)t * kResultSub, src, sizeof(DevResultSlot) * kResultSub, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaEventRecord(b->result_done[t], b->stream));
+  // read it on the copy stream, behind an event recorded after the launch: the next fan-out does not queue behind this D2H
+  CK(cudaEventRecord(b->launched, b->stream));
+  CK(cudaStreamWaitEvent(b->copy_stream, b->launched, 0));
+  CK(cudaMemcpyAsync(b->h_result + (size_t)t * kResultSub, src, sizeof(DevResultSlot) * kResultSub, cudaMemcpyDeviceToHost, b->copy_stream));
+  CK(cudaEventRecord(b->result_done[t], b->copy_stream));
   *ticket = t;
   return CPBUS_OK;
 }
