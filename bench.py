@@ -359,7 +359,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = (json.load(open(tp)).get(args.workload) or {}).get(str(B))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
