@@ -351,7 +351,10 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     d_local = (st1["deliveries"] - st0["deliveries"]) / steps        # records per launch on this GPU
-    per_sub_state = 4 + 16 + (16 if not args.no_digest else 0) + (64 if K_timers else 0)   # mask + tail r/w (+ digest r/w) (+ timer slot r/w)
+    # algorithmic bytes per launch: every delivered record is one 32-byte sector; every mailbox's 32-byte
+    # control block is read once and written once; an armed timer slot costs its 16-byte hot half read plus, when it fires,
+    # the cold half read and both halves written (~64 B); the batch itself is read once from HBM
+    per_sub_state = 64 + (64 if K_timers else 0)
     alg_bytes = 32.0 * d_local + n_subs * per_sub_state + B * 32
     kernel_ms = float(e0.elapsed_time(e1)) / steps                    # this rank's launches are back to back on the stream
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
