@@ -127,18 +127,11 @@ def run_reference(args):
     n_subs = args.subs or wl["subs"]
     cores = os.cpu_count() or 1
     steps = args.steps or 8
-    probe = ob.gobus_bench(n_subs, 4, 1000, cores)
-    per_step_events = int(max(args.batch, min(50_000, probe * 10.0 / n_subs)))       # ~10 s per step
-    per_step_events = max(args.batch, per_step_events // max(1, steps + args.warmup))
-    for _ in range(max(0, min(args.warmup, 2))):
-        ob.gobus_bench(n_subs, per_step_events, 1000, cores)
-    t0 = time.perf_counter()
-    total = 0.0
-    for _ in range(steps):
-        total += n_subs * per_step_events
-        ob.gobus_bench(n_subs, per_step_events, 1000, cores)
-    dt = time.perf_counter() - t0
-    value = total / dt
+    warmup = max(0, args.warmup)
+    probe = ob.gobus_bench(n_subs, 4, 1000, cores)                    # deliveries/s estimate, to size the per-step sample
+    budget_s = 45.0                                                   # the whole --steps K --warmup W run ends within about a minute
+    per_step_events = int(max(1, min(50_000, probe * budget_s / n_subs / (steps + warmup))))
+    value, dt = ob.gobus_bench_steps(n_subs, per_step_events, steps, warmup, 1000, cores)
     line = {"impl": "reference", "metric": "events/sec through Bus.Publish (deliveries/s)", "value": value,
             "unit": "deliveries/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -100,6 +100,9 @@ uint64_t orc_digest_multiplier(void);
  *      cost model, NOT a checker.  Returns deliveries per second. ---- */
 double gobus_bench(uint32_t n_subs, uint32_t n_events, uint32_t mailbox_cap,
                    uint32_t n_threads, uint64_t* checksum_out);
+/* step-structured variant (threads/channels created once; `warmup` untimed steps, then `steps` timed ones) */
+double gobus_bench_steps(uint32_t n_subs, uint32_t events_per_step, uint32_t steps, uint32_t warmup, uint32_t mailbox_cap,
+                         uint32_t n_threads, double* seconds_out);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@
  * parallelism than the Go bus has (its lock serialises publishers), i.e. a
  * generous baseline.
  */
+#define _POSIX_C_SOURCE 200809L   /* pthread_barrier_t, clock_gettime under -std=c11 */
 #include "cpbus_oracle.h"
 
 #include <pthread.h>
@@ -129,6 +130,85 @@ double gobus_bench(uint32_t n_subs, uint32_t n_events, uint32_t mailbox_cap,
   uint64_t sum = 0, deliv = 0;
   for (uint32_t t = 0; t < n_threads; t++) { sum += sh[t].checksum; deliv += sh[t].deliveries; }
   if (checksum_out) *checksum_out = sum ^ deliv;
+  for (uint32_t s = 0; s < n_subs; s++) { free(all[s]->buf); free(all[s]); }
+  free(all); free(sh); free(th); free(trace);
+  return sec > 0 ? (double)deliv / sec : 0.0;
+}
+
+/* ---- step-structured run for `bench.py --impl reference`: channels and threads are created ONCE; every step
+ *      publishes `events_per_step` events to every subscriber (shards in parallel, a barrier between steps);
+ *      `warmup` steps are untimed.  Returns deliveries per second over the timed steps. ---- */
+typedef struct step_shard {
+  go_chan** subs; uint32_t n, events_per_step, steps, warmup; const go_event* trace; uint32_t trace_len;
+  pthread_barrier_t* bar; struct timespec* t0; struct timespec* t1; int lead; uint64_t checksum, deliveries;
+} step_shard;
+
+static void* run_step_shard(void* arg) {
+  step_shard* sh = (step_shard*)arg;
+  uint64_t sum = 0, deliv = 0;
+  uint32_t pos = 0;
+  for (uint32_t st = 0; st < sh->warmup + sh->steps; st++) {
+    if (st == sh->warmup) {
+      pthread_barrier_wait(sh->bar);
+      if (sh->lead) clock_gettime(CLOCK_MONOTONIC, sh->t0);
+      deliv = 0;
+    }
+    for (uint32_t i = 0; i < sh->events_per_step; i++) {
+      const go_event* e = &sh->trace[pos]; if (++pos == sh->trace_len) pos = 0;
+      for (uint32_t s = 0; s < sh->n; s++) {
+        go_chan* c = sh->subs[s];
+        while (!chansend(c, e)) {
+          for (uint32_t d = 0; d < sh->n; d++) { go_event got; while (chanrecv(sh->subs[d], &got)) { sum += (uint64_t)got.code * 31u + (uint64_t)got.len; deliv++; } }
+        }
+      }
+    }
+    /* the consumers run at the end of every step: nothing is left queued across the timing boundary */
+    for (uint32_t d = 0; d < sh->n; d++) { go_event got; while (chanrecv(sh->subs[d], &got)) { sum += (uint64_t)got.code * 31u + (uint64_t)got.len; deliv++; } }
+    pthread_barrier_wait(sh->bar);
+  }
+  if (sh->lead) clock_gettime(CLOCK_MONOTONIC, sh->t1);
+  sh->checksum = sum; sh->deliveries = deliv;
+  return NULL;
+}
+
+double gobus_bench_steps(uint32_t n_subs, uint32_t events_per_step, uint32_t steps, uint32_t warmup, uint32_t mailbox_cap,
+                         uint32_t n_threads, double* seconds_out) {
+  if (!n_subs || !events_per_step || !steps || !mailbox_cap) return 0.0;
+  if (n_threads == 0) n_threads = 1;
+  if (n_threads > n_subs) n_threads = n_subs;
+  static const char* const SRC[4] = { "global", "myjob", "SIGHUP", "watch.backend" };
+  const uint32_t trace_len = 4096;
+  go_event* trace = (go_event*)malloc((size_t)trace_len * sizeof(go_event));
+  uint64_t x = 0xC0DEB200ull;
+  for (uint32_t i = 0; i < trace_len; i++) {
+    x += 0x9E3779B97F4A7C15ull; uint64_t z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z ^= z >> 27;
+    trace[i].code = 1 + (int64_t)(z % 16); trace[i].src = SRC[(z >> 8) & 3]; trace[i].len = (int64_t)strlen(trace[i].src);
+  }
+  go_chan** all = (go_chan**)malloc((size_t)n_subs * sizeof(go_chan*));
+  for (uint32_t s = 0; s < n_subs; s++) {
+    go_chan* c = (go_chan*)calloc(1, sizeof(go_chan));
+    c->dataqsiz = mailbox_cap; c->buf = (go_event*)calloc(mailbox_cap, sizeof(go_event));
+    atomic_flag_clear(&c->lock);
+    all[s] = c;
+  }
+  pthread_barrier_t bar; pthread_barrier_init(&bar, NULL, n_threads);
+  struct timespec t0, t1;
+  step_shard* sh = (step_shard*)calloc(n_threads, sizeof(step_shard));
+  pthread_t* th = (pthread_t*)malloc(n_threads * sizeof(pthread_t));
+  uint32_t per = n_subs / n_threads, extra = n_subs % n_threads, off = 0;
+  for (uint32_t t = 0; t < n_threads; t++) {
+    sh[t].n = per + (t < extra); sh[t].subs = all + off; off += sh[t].n;
+    sh[t].events_per_step = events_per_step; sh[t].steps = steps; sh[t].warmup = warmup; sh[t].trace = trace; sh[t].trace_len = trace_len;
+    sh[t].bar = &bar; sh[t].t0 = &t0; sh[t].t1 = &t1; sh[t].lead = (t == 0);
+  }
+  for (uint32_t t = 1; t < n_threads; t++) pthread_create(&th[t], NULL, run_step_shard, &sh[t]);
+  run_step_shard(&sh[0]);
+  for (uint32_t t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
+  double sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  uint64_t deliv = 0;
+  for (uint32_t t = 0; t < n_threads; t++) deliv += sh[t].deliveries;
+  if (seconds_out) *seconds_out = sec;
+  pthread_barrier_destroy(&bar);
   for (uint32_t s = 0; s < n_subs; s++) { free(all[s]->buf); free(all[s]); }
   free(all); free(sh); free(th); free(trace);
   return sec > 0 ? (double)deliv / sec : 0.0;

@@ -36,6 +36,7 @@ def lib():
             "orc_code_from_string": (C.c_int, [C.c_char_p]), "orc_record_hash": (u64, [vp]),
             "orc_digest_multiplier": (u64, []),
             "gobus_bench": (C.c_double, [u32, u32, u32, u32, C.POINTER(u64)]),
+            "gobus_bench_steps": (C.c_double, [u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -140,3 +141,10 @@ class Oracle:
 def gobus_bench(n_subs, n_events, mailbox_cap=1000, n_threads=1):
     chk = C.c_uint64()
     return lib().gobus_bench(n_subs, n_events, mailbox_cap, n_threads, C.byref(chk))
+
+
+def gobus_bench_steps(n_subs, events_per_step, steps, warmup, mailbox_cap=1000, n_threads=1):
+    """(deliveries/s, seconds) over `steps` timed steps; threads and channels are created once."""
+    sec = C.c_double()
+    v = lib().gobus_bench_steps(n_subs, events_per_step, steps, warmup, mailbox_cap, n_threads, C.byref(sec))
+    return v, sec.value
