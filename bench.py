@@ -229,10 +229,11 @@ def main():
     if world > 1:
         ingest_mode = "nccl-broadcast"
         if not os.environ.get("CPBUS_BENCH_NCCL_INGEST"):
-            try:
-                # the publisher's stream lives in a cpbus_shared_alloc buffer; the other ranks map it (CUDA IPC, NVLink)
-                box = [None]
-                if rank == 0:
+            # the publisher's stream lives in a cpbus_shared_alloc buffer; the other ranks map it (CUDA IPC, NVLink).
+            # Every rank reaches both collectives below whatever happens locally, so a failure cannot hang the job.
+            local_ok, handle = 1, None
+            if rank == 0:
+                try:
                     shared_ptr, handle = bus.shared_alloc(n_ev * 32)
 
                     class _Raw:                                        # zero-copy torch view of the shared buffer
@@ -242,17 +243,26 @@ def main():
                     trace_dev = shared_view
                     trace_q = trace_dev.view(torch.int64).view(n_ev, 4)
                     torch.cuda.synchronize()
-                    box = [handle]
-                dist.broadcast_object_list(box, src=0)
-                if rank != 0:
-                    peer_trace = bus.shared_open(box[0])
-                ok_t = torch.tensor([1], device=dev)
-                dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
-                if int(ok_t.item()) == 1:
-                    ingest_mode = "nvlink-peer-pull (fused into the fan-out kernel)"
-            except Exception as ex:                                    # pragma: no cover - depends on the box
-                print(f"[bench] peer mapping unavailable ({ex!r}); falling back to NCCL broadcast", file=sys.stderr)
-                peer_trace = None
+                except Exception as ex:                                # pragma: no cover - depends on the box
+                    print(f"[bench] shared stream buffer unavailable ({ex!r})", file=sys.stderr)
+                    local_ok, handle = 0, None
+            box = [handle]
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                if box[0] is None:
+                    local_ok = 0
+                else:
+                    try:
+                        peer_trace = bus.shared_open(box[0])
+                    except Exception as ex:                            # pragma: no cover
+                        print(f"[bench] peer mapping unavailable ({ex!r})", file=sys.stderr)
+                        local_ok, peer_trace = 0, None
+            ok_t = torch.tensor([local_ok], device=dev)
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+            if int(ok_t.item()) == 1:
+                ingest_mode = "nvlink-peer-pull (fused into the fan-out kernel)"
+            elif rank == 0:
+                print("[bench] falling back to NCCL broadcast of the event stream", file=sys.stderr)
         src_ptr = peer_trace if (peer_trace is not None and ingest_mode.startswith("nvlink")) else trace_dev.data_ptr()
     else:
         src_ptr = trace_dev.data_ptr()
