@@ -138,10 +138,11 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
 
 template <int STORE, bool TIMERS, bool DIGEST>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
+  static bool attr_done[64] = {};   // per instantiation AND per device: function attributes are per-device state
+  const int dev = b->device & 63;
+  if (!attr_done[dev]) {
     CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (!grid) {
     // Several waves of short-lived CTAs rather than one persistent wave: the hardware CTA scheduler
