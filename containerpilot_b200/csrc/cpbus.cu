@@ -93,6 +93,9 @@ struct cpbus {
   // registry mirror (events/bus.go:13 `registry map[*Subscriber]bool`)
   std::vector<uint32_t> h_mask;
   std::vector<uint8_t> h_active;
+  uint32_t* d_order = nullptr;            // active subscribers sorted by code mask (ORDERED fan-out)
+  uint32_t n_order = 0, n_filtered = 0;   // n_filtered: active subscribers whose mask is not CPBUS_MASK_ALL
+  bool order_dirty = true, use_order = true;
   std::vector<size_t> oneshot_idx;        // armed one-shot timers (index into h_timers)
   std::vector<HostTimer> h_timers;        // N*K, allocated on first timer
   uint32_t n_next = 0, n_active = 0, n_timers = 0;
@@ -115,6 +118,9 @@ struct cpbus {
 
 namespace {
 
+// counting sort of the active subscribers by their 17-bit code mask (stable: ids ascending inside a mask)
+int rebuild_order(cpbus* b);
+
 int dev_guard(cpbus* b) {
   CK(cudaSetDevice(b->device));
   return CPBUS_OK;
@@ -136,12 +142,27 @@ void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
   if (old != -1 && b->dbg_head == b->dbg_tail) b->dbg_tail = (b->dbg_tail + 1) % 10;
 }
 
-template <int STORE, bool TIMERS, bool DIGEST>
+int rebuild_order(cpbus* b) {
+  std::vector<uint32_t> count((size_t)CPBUS_MASK_ALL + 2, 0);
+  for (uint32_t i = 0; i < b->n_next; i++) if (b->h_active[i]) count[(b->h_mask[i] & CPBUS_MASK_ALL) + 1]++;
+  for (size_t k = 1; k < count.size(); k++) count[k] += count[k - 1];
+  std::vector<uint32_t> order(count.back());
+  for (uint32_t i = 0; i < b->n_next; i++) if (b->h_active[i]) order[count[b->h_mask[i] & CPBUS_MASK_ALL]++] = i;
+  b->n_order = (uint32_t)order.size();
+  if (b->n_order) {
+    CK(cudaMemcpyAsync(b->d_order, order.data(), (size_t)b->n_order * 4, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
+  b->order_dirty = false;
+  return CPBUS_OK;
+}
+
+template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done[64] = {};   // per instantiation AND per device: function attributes are per-device state
   const int dev = b->device & 63;
   if (!attr_done[dev]) {
-    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST, ORDERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done[dev] = true;
   }
   if (!grid) {
@@ -167,7 +188,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the next fan-out's prologue overlaps this one's tail
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = b->pdl ? 1 : 0;
-  CK(cudaLaunchKernelEx(&cfg, fanout_kernel<STORE, TIMERS, DIGEST>, p));
+  CK(cudaLaunchKernelEx(&cfg, fanout_kernel<STORE, TIMERS, DIGEST, ORDERED>, p));
   CK(cudaGetLastError());
   return CPBUS_OK;
 }
@@ -198,13 +219,27 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
-  const int variant = (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0);
-#define CPBUS_DISPATCH(ST)                                                         \
-  switch (variant) {                                                              \
-    case 0: rc = launch_fanout_t<ST, false, false>(b, p, grid, smem); break;      \
-    case 1: rc = launch_fanout_t<ST, false, true>(b, p, grid, smem); break;       \
-    case 2: rc = launch_fanout_t<ST, true, false>(b, p, grid, smem); break;       \
-    default: rc = launch_fanout_t<ST, true, true>(b, p, grid, smem); break;       \
+  // ORDERED build (no timers armed, at least one filtered subscriber): walk the mailboxes in code-mask order so that
+  // equal masks are neighbours and share one filter pass (cost ~ deliveries + distinct masks, not subscribers x events)
+  if (!p.timers_on && b->use_order && b->n_filtered > 0) {
+    if (b->order_dirty) { int orc_ = rebuild_order(b); if (orc_) return orc_; }
+    if (b->n_order) {
+      const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
+      uint32_t spw = b->subs_per_warp ? std::min(32u, b->subs_per_warp) : std::max(4u, 16u / scale);   // measured: 8 at 512-event batches
+      p.order = b->d_order; p.n_order = b->n_order; p.spw = spw;
+      const uint32_t warps = (b->n_order + spw - 1) / spw;
+      grid = std::max(1u, (warps + kWarpsPerCta - 1) / kWarpsPerCta);
+    }
+  }
+  const int variant = (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0) | (p.order ? 4 : 0);
+#define CPBUS_DISPATCH(ST)                                                                \
+  switch (variant) {                                                                     \
+    case 0: rc = launch_fanout_t<ST, false, false, false>(b, p, grid, smem); break;      \
+    case 1: rc = launch_fanout_t<ST, false, true, false>(b, p, grid, smem); break;       \
+    case 2: rc = launch_fanout_t<ST, true, false, false>(b, p, grid, smem); break;       \
+    case 3: rc = launch_fanout_t<ST, true, true, false>(b, p, grid, smem); break;        \
+    case 4: rc = launch_fanout_t<ST, false, false, true>(b, p, grid, smem); break;       \
+    default: rc = launch_fanout_t<ST, false, true, true>(b, p, grid, smem); break;       \
   }
   switch (b->store) {
     case CPBUS_STORE_V4: CPBUS_DISPATCH(CPBUS_STORE_V4); break;
@@ -370,6 +405,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  if (const char* e = getenv("CPBUS_ORDER")) b->use_order = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_PDL")) b->pdl = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_ZERO_COPY")) b->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);
@@ -394,7 +430,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     return fail(CPBUS_ENOMEM);                                                                \
   }
   ALLOC(b->d_ring, N * R * sizeof(cpbus_event));
-  ALLOC(b->d_ctl, N * sizeof(SubCtl));
+  ALLOC(b->d_ctl, N * sizeof(SubCtl)); ALLOC(b->d_order, N * 4);
   if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
   ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32 * cpbus::kFoldSlots); ALLOC(b->d_pow, kPowTableLen * 8);
   ALLOC(b->d_desc, 2 * fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 256);
@@ -444,7 +480,7 @@ int cpbus_destroy(cpbus_t* b) {
   if (!b) return CPBUS_EINVAL;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->d_ring); cudaFree(b->d_ctl);
+  cudaFree(b->d_ring); cudaFree(b->d_ctl); cudaFree(b->d_order);
   cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
   if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
   for (int i = 0; i < cpbus::kStage; i++) {
@@ -503,10 +539,11 @@ int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t
     b->h_mask[first + i] = (masks ? masks[i] : CPBUS_MASK_ALL) & CPBUS_MASK_ALL;
     blocks[i].mask = b->h_mask[first + i] | kActiveBit;
     b->h_active[first + i] = 1;
+    if (b->h_mask[first + i] != CPBUS_MASK_ALL) b->n_filtered++;
   }
   CK(cudaMemcpyAsync(b->d_ctl + first, blocks.data(), (size_t)n * sizeof(SubCtl), cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
-  b->n_next += n; b->n_active += n;
+  b->n_next += n; b->n_active += n; b->order_dirty = true;
   if (first_sub_id) *first_sub_id = b->cfg.sub_id_base + first;
   return CPBUS_OK;
 }
@@ -522,6 +559,8 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   // second Unsubscribe drives the WaitGroup negative in Go (events/bus.go:121) => panic
   if (!b->h_active[l]) return CPBUS_ECLOSED;
   b->h_active[l] = 0;
+  if (b->h_mask[l] != CPBUS_MASK_ALL) b->n_filtered--;
+  b->order_dirty = true;
   const uint32_t word = 0;
   CK(cudaMemcpyAsync(&b->d_ctl[l].mask, &word, 4, cudaMemcpyHostToDevice, b->stream));
   if (b->K && !b->h_timers.empty()) {

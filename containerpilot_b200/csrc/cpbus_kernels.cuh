@@ -86,6 +86,8 @@ struct FanoutParams {
   cpbus_event* prefetch_dst;         // local buffer it is pulled into while this launch's stores are in flight
   uint32_t prefetch_n;
   uint32_t batch_dep;         // 1: `batch` was produced by the previous launch (prefetch buffer): wait for it before staging
+  const uint32_t* order;      // ORDERED build: active subscribers sorted by code mask (equal masks are neighbours)
+  uint32_t n_order, spw;      // ... how many, and how many consecutive positions each warp takes (<= 32)
   uint64_t w_now;             // watermark: timers due <= w_now fire in this launch
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
@@ -237,7 +239,10 @@ __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
 
 // TIMERS=false compiles every timer/tick path out (the host knows when no timer is armed): fewer registers,
 // one more resident CTA per SM.
-template <int STORE, bool TIMERS, bool DIGEST>
+// ORDERED (no-timer build only): warps walk the subscribers in code-mask order, so a run of mailboxes with the same
+// mask shares one match/compaction pass and one digest polynomial — filtered fan-out then costs one copy per mailbox
+// plus one filter pass per DISTINCT mask in the warp's block, instead of a filter pass per mailbox.
+template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED>
 __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
@@ -359,13 +364,21 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
   const bool timers_on = TIMERS && p.timers_on && K;
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
-  uint32_t s = blockIdx.x * kWarpsPerCta + warp;
+  // position space: plain build = subscriber index, strided over the grid; ORDERED build = index into p.order, one
+  // contiguous block of p.spw positions per warp (lane l keeps the id at block position l: one coalesced load)
+  uint32_t pos = ORDERED ? (blockIdx.x * kWarpsPerCta + warp) * p.spw : blockIdx.x * kWarpsPerCta + warp;
+  const uint32_t pos_end = ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs;
+  const uint32_t pos_step = ORDERED ? 1u : wstride;
+  uint32_t my_ids = 0;
+  if (ORDERED && pos + lane < pos_end) my_ids = __ldg(p.order + pos + lane);
+  const uint32_t pos0 = pos;
+  uint32_t s = ORDERED ? __shfl_sync(0xffffffffu, my_ids, 0) : pos;
   // ---- from here on the previous launch's results are needed: wait for it, then let the NEXT launch start its prologue
   // (the trigger comes after the wait so that a launch can never overlap its grand-parent: two descriptor buffers suffice)
   if (!p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
-  if (s < p.n_subs) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
+  if (pos < pos_end) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
     ld_sector(p.ctl + s, ca, cb, keep);
     if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
   }
@@ -379,11 +392,15 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
 
   // software pipeline: the control block (and timer slot) of the NEXT subscriber is in flight
   // while the current one is being written, so no DRAM round trip is exposed per subscriber
-  for (; s < p.n_subs; s += wstride) {
+  uint32_t run_mask = 0xffffffffu, run_k = 0;   // ORDERED: the filter pass of the previous mailbox, reusable while the mask repeats
+  uint64_t run_sum = 0;
+  for (; pos < pos_end; pos += pos_step) {
     const uint4 cur_a = ca, cur_b = cb, cur_ta = ta;
+    if (ORDERED) s = __shfl_sync(0xffffffffu, my_ids, (pos - pos0) & 31); else s = pos;
     {
-      const uint32_t sn = s + wstride;
-      if (sn < p.n_subs) {
+      const uint32_t pn = pos + pos_step;
+      if (pn < pos_end) {
+        const uint32_t sn = ORDERED ? __shfl_sync(0xffffffffu, my_ids, (pn - pos0) & 31) : pn;
         ld_sector(p.ctl + sn, ca, cb, keep);
         if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)sn * K + tk_slot, ta, keep);
       }
@@ -509,50 +526,60 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         // ================= filtered run: compact the matching event indices, then an output-centric copy =================
         // pass 1: ballot 32 events at a time; matching lanes append their event index to the warp's scratch list
         uint16_t* my_idx = reinterpret_cast<uint16_t*>(my_tick);
-        uint32_t base = 0;
-        const uint32_t nchunks = (n + 31) >> 5;
-        // code bits of 4 chunks are fetched up front: 4 independent shared-memory loads in flight instead of a
-        // load -> test -> ballot chain per chunk (46 % of this path's stall samples were short-scoreboard on that load)
-        for (uint32_t c0 = 0; c0 < nchunks; c0 += 4) {
-          uint32_t cbit[4];
+        const bool reuse = ORDERED && (m & CPBUS_MASK_ALL) == run_mask;   // same mask as the previous mailbox of this warp
+        if (!reuse) {
+          uint32_t base = 0;
+          const uint32_t nchunks = (n + 31) >> 5;
+          // code bits of 4 chunks are fetched up front: 4 independent shared-memory loads in flight instead of a
+          // load -> test -> ballot chain per chunk (46 % of this path's stall samples were short-scoreboard on that load)
+          for (uint32_t c0 = 0; c0 < nchunks; c0 += 4) {
+            uint32_t cbit[4];
 #pragma unroll
-          for (uint32_t u = 0; u < 4; u++) {
-            const uint32_t i = (c0 + u) * 32 + lane;
-            cbit[u] = i < n ? s_meta[i].x : 0u;
-          }
+            for (uint32_t u = 0; u < 4; u++) {
+              const uint32_t i = (c0 + u) * 32 + lane;
+              cbit[u] = i < n ? s_meta[i].x : 0u;
+            }
 #pragma unroll
-          for (uint32_t u = 0; u < 4; u++) {
-            const bool match = (m & cbit[u]) != 0;
-            const uint32_t w = __ballot_sync(0xffffffffu, match);
-            if (match) my_idx[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((c0 + u) * 32 + lane);
-            base += __popc(w);
+            for (uint32_t u = 0; u < 4; u++) {
+              const bool match = (m & cbit[u]) != 0;
+              const uint32_t w = __ballot_sync(0xffffffffu, match);
+              if (match) my_idx[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((c0 + u) * 32 + lane);
+              base += __popc(w);
+            }
           }
+          run_k = base;
+          __syncwarp();
         }
-        k = base;
-        __syncwarp();
+        k = run_k;
         // pass 2: lane -> output slot, so stores are fully coalesced and only ceil(k/32) iterations run.
         // Digest by per-lane Horner in P^32: acc_l = sum_it H(e) (P^32)^(nit_l-1-it); one power lookup per lane at the end.
         uint64_t acc = 0;
         const uint64_t p32 = s_pow[32];
+        const bool hashing = DIGEST && !reuse;
         uint32_t o = lane;
         for (; o + 32 < k; o += 64) {   // two outputs per lane per iteration: their index/record/hash loads are independent
           const uint32_t i0 = my_idx[o], i1 = my_idx[o + 32];
           const uint4 a0 = s4[2 * i0], b0 = s4[2 * i0 + 1], a1 = s4[2 * i1], b1 = s4[2 * i1 + 1];
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
           st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
-          if (DIGEST) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
+          if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
         }
         for (; o < k; o += 32) {
           const uint32_t i = my_idx[o];
           const uint4 a = s4[2 * i], b = s4[2 * i + 1];
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
-          if (DIGEST) acc = acc * p32 + s_rhash[i];
+          if (hashing) acc = acc * p32 + s_rhash[i];
         }
         if (DIGEST) {
-          // o is now the first index this lane did NOT write; its last one was o-32 (if any)
-          dsum = (o >= 32 && o - 32 < k) ? acc * s_pow[k - 1 - (o - 32)] : 0ull;
-          dsum = warp_sum64(dsum);
+          if (reuse) dsum = run_sum;
+          else {
+            // o is now the first index this lane did NOT write; its last one was o-32 (if any)
+            dsum = (o >= 32 && o - 32 < k) ? acc * s_pow[k - 1 - (o - 32)] : 0ull;
+            dsum = warp_sum64(dsum);
+            if (ORDERED) run_sum = dsum;
+          }
         }
+        if (ORDERED) run_mask = m & CPBUS_MASK_ALL;
         __syncwarp();
       } else {
         // timers build: register budget is tighter (80, no spills) — single pass, ballot + running rank
