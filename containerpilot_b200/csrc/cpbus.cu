@@ -222,7 +222,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   // ORDERED build (no timers armed, at least one filtered subscriber): walk the mailboxes in code-mask order so that
   // equal masks are neighbours and share one filter pass (cost ~ deliveries + distinct masks, not subscribers x events)
   if (!p.timers_on && b->use_order && b->n_filtered > 0) {
-    if (b->order_dirty) { int orc_ = rebuild_order(b); if (orc_) return orc_; }
+    if (b->order_dirty) { const int rc_order = rebuild_order(b); if (rc_order) return rc_order; }
     if (b->n_order) {
       const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
       uint32_t spw = b->subs_per_warp ? std::min(32u, b->subs_per_warp) : std::max(4u, 16u / scale);   // measured: 8 at 512-event batches
