@@ -8,6 +8,7 @@
 #include "cpbus_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +68,7 @@ struct cpbus {
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
   bool pdl = true;                        // programmatic dependent launch of consecutive fan-outs
+  int h2d_spin_us = 30;                   // how long cpbus_flush waits on the host for the batch's H2D before inserting a stream wait
   bool zero_copy = false;                 // fan-out pulls host-staged batches straight from pinned memory (experiment: CPBUS_ZERO_COPY=1)
   cudaEvent_t launched = nullptr;         // recorded after the latest fan-out (step results are read on the copy stream)
   int hints = -1;                         // -1 auto; bit0: control blocks / timer slots evict_last in L2
@@ -74,12 +76,18 @@ struct cpbus {
   unsigned long long* d_fold = nullptr;   // kFoldSlots x 4 words
   cudaEvent_t fold_done[kFoldSlots] = {};
   uint32_t fold_next = 0;
-  static constexpr int kStage = 4;         // staging ring: the host may run 3 flushes ahead of the GPU
-  cpbus_event* d_batch[kStage] = {};
+  static constexpr int kStage = 8;         // staging ring: the host may run several flushes ahead of the GPU
+  static constexpr int kEpoch = 4;         // a `consumed` event is recorded only after every kEpoch-th buffer, so that most
+                                           // consecutive fan-outs are adjacent in the stream (programmatic dependent launch)
+  static constexpr int kDevSlots = 64, kDevEpoch = 16;
+  cpbus_event* d_stage = nullptr;          // kDevSlots x batch_cap records: device side of the staging ring
+  cudaEvent_t epoch_done[kDevSlots / kDevEpoch] = {};   // on the bus stream, after the last fan-out of each epoch of slots
+  uint32_t dev_slot = 0;
   cpbus_event* h_batch[kStage] = {};       // pinned staging
   cudaEvent_t h2d_done[kStage] = {};       // on copy_stream: batch c has reached HBM
   cudaEvent_t consumed[kStage] = {};       // on the bus stream: the fan-out that read d_batch[c] has finished
   cudaStream_t copy_stream = nullptr;      // H2D of batch i+1 overlaps the fan-out of batch i
+  cudaStream_t result_stream = nullptr;    // D2H of step results: must not queue in front of the next batch's H2D
   // per-launch results written by the fan-out kernel itself (no extra kernel to read a step's result)
   DevResultSlot* d_result = nullptr;       // kResultRing x kResultSub slots
   DevResultSlot* h_result = nullptr;       // pinned, kFoldSlots tickets x kResultSub
@@ -293,25 +301,40 @@ int flush_staged(cpbus* b, uint64_t w) {
     // batch over PCIe in its prologue (the staged path) — no H2D op, no stream waits, consecutive fan-outs stay adjacent.
     rc = launch_fanout(b, b->h_batch[c], n, w, /*staged=*/true);
     if (rc) return rc;
-    CK(cudaEventRecord(b->consumed[c], b->stream));
+    if ((c & (cpbus::kEpoch - 1)) == cpbus::kEpoch - 1) CK(cudaEventRecord(b->consumed[c], b->stream));
     b->n_staged = 0;
     b->cur = (b->cur + 1) % cpbus::kStage;
-    CK(cudaEventSynchronize(b->consumed[b->cur]));   // the launch that read the buffer we are about to overwrite has finished
+    CK(cudaEventSynchronize(b->consumed[b->cur | (cpbus::kEpoch - 1)]));   // the launch that read the buffer we are about to overwrite has finished
     return CPBUS_OK;
   }
+  // Device staging is a long ring (kDevSlots batches): a slot is reused only kDevSlots flushes later, far beyond how far the
+  // host can run ahead, so the H2D never has to wait for an old fan-out and lands within microseconds.  Reuse safety is a
+  // host-side check once per epoch of kDevEpoch slots (almost always already satisfied).
+  const uint32_t slot = b->dev_slot;
+  cpbus_event* d_dst = b->d_stage + (size_t)slot * b->B;
+  if (slot % cpbus::kDevEpoch == 0) CK(cudaEventSynchronize(b->epoch_done[slot / cpbus::kDevEpoch]));   // last round's users of this epoch are done
   if (n) {
-    CK(cudaStreamWaitEvent(b->copy_stream, b->consumed[c], 0));   // the previous user of d_batch[c] is done
-    CK(cudaMemcpyAsync(b->d_batch[c], b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->copy_stream));
+    CK(cudaMemcpyAsync(d_dst, b->h_batch[c], (size_t)n * sizeof(cpbus_event), cudaMemcpyHostToDevice, b->copy_stream));
     CK(cudaEventRecord(b->h2d_done[c], b->copy_stream));
-    CK(cudaStreamWaitEvent(b->stream, b->h2d_done[c], 0));
+    // Give the 8-16 KiB copy a few microseconds to land.  If it has, the bus stream needs no wait node, consecutive fan-outs
+    // stay adjacent in the stream and the next launch's prologue overlaps this one's tail (programmatic dependent launch).
+    bool landed = false;
+    const auto t_spin = std::chrono::steady_clock::now();
+    do {
+      const cudaError_t q = cudaEventQuery(b->h2d_done[c]);
+      if (q == cudaSuccess) { landed = true; break; }
+      if (q != cudaErrorNotReady) { CK(q); }
+    } while (std::chrono::steady_clock::now() - t_spin < std::chrono::microseconds(b->h2d_spin_us));
+    if (!landed) CK(cudaStreamWaitEvent(b->stream, b->h2d_done[c], 0));
   }
   bool ok = true;
-  rc = admit(b, b->d_batch[c], n, w, &ok);
+  rc = admit(b, d_dst, n, w, &ok);
   if (rc) return rc;
   if (!ok) return CPBUS_EAGAIN;   // staged events stay staged; drain and call flush again
-  rc = launch_fanout(b, b->d_batch[c], n, w);
+  rc = launch_fanout(b, d_dst, n, w);
   if (rc) return rc;
-  CK(cudaEventRecord(b->consumed[c], b->stream));
+  if (slot % cpbus::kDevEpoch == cpbus::kDevEpoch - 1) CK(cudaEventRecord(b->epoch_done[slot / cpbus::kDevEpoch], b->stream));
+  b->dev_slot = (slot + 1) % cpbus::kDevSlots;
   b->n_staged = 0;
   b->cur = (b->cur + 1) % cpbus::kStage;
   CK(cudaEventSynchronize(b->h2d_done[b->cur]));   // the pinned buffer we are about to overwrite has left the host
@@ -405,6 +428,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
+  if (const char* e = getenv("CPBUS_H2D_SPIN_US")) b->h2d_spin_us = atoi(e);
   if (const char* e = getenv("CPBUS_ORDER")) b->use_order = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_PDL")) b->pdl = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_ZERO_COPY")) b->zero_copy = atoi(e) != 0;
@@ -436,9 +460,12 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_desc, 2 * fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 256);
   if (cudaMemsetAsync(b->d_desc_ready, 0, 256, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (cudaStreamCreateWithFlags(&b->result_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaEventCreateWithFlags(&b->launched, cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
+  ALLOC(b->d_stage, (size_t)cpbus::kDevSlots * B * sizeof(cpbus_event));
+  for (int i = 0; i < cpbus::kDevSlots / cpbus::kDevEpoch; i++)
+    if (cudaEventCreateWithFlags(&b->epoch_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   for (int i = 0; i < cpbus::kStage; i++) {
-    ALLOC(b->d_batch[i], (size_t)B * sizeof(cpbus_event));
     if (cudaMallocHost((void**)&b->h_batch[i], (size_t)B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
     if (cudaEventCreateWithFlags(&b->h2d_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
     if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
@@ -483,12 +510,14 @@ int cpbus_destroy(cpbus_t* b) {
   cudaFree(b->d_ring); cudaFree(b->d_ctl); cudaFree(b->d_order);
   cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
   if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+  if (b->result_stream) { cudaStreamSynchronize(b->result_stream); cudaStreamDestroy(b->result_stream); }
   for (int i = 0; i < cpbus::kStage; i++) {
-    cudaFree(b->d_batch[i]);
     if (b->h_batch[i]) cudaFreeHost(b->h_batch[i]);
     if (b->h2d_done[i]) cudaEventDestroy(b->h2d_done[i]);
     if (b->consumed[i]) cudaEventDestroy(b->consumed[i]);
   }
+  cudaFree(b->d_stage);
+  for (int i = 0; i < cpbus::kDevSlots / cpbus::kDevEpoch; i++) if (b->epoch_done[i]) cudaEventDestroy(b->epoch_done[i]);
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->launched) cudaEventDestroy(b->launched);
   cudaFree(b->d_drain); cudaFree(b->d_drain_idx);
@@ -943,11 +972,12 @@ int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) {
   int rc = dev_guard(b); if (rc) return rc;
   const uint32_t t = b->result_next++ % 8;
   const DevResultSlot* src = b->d_result + (size_t)(b->launch_seq % kResultRing) * kResultSub;
-  // read it on the copy stream, behind an event recorded after the launch: the next fan-out does not queue behind this D2H
+  // read it on a side stream, behind an event recorded after the launch: neither the next fan-out nor the next batch's
+  // H2D queues behind this D2H
   CK(cudaEventRecord(b->launched, b->stream));
-  CK(cudaStreamWaitEvent(b->copy_stream, b->launched, 0));
-  CK(cudaMemcpyAsync(b->h_result + (size_t)t * kResultSub, src, sizeof(DevResultSlot) * kResultSub, cudaMemcpyDeviceToHost, b->copy_stream));
-  CK(cudaEventRecord(b->result_done[t], b->copy_stream));
+  CK(cudaStreamWaitEvent(b->result_stream, b->launched, 0));
+  CK(cudaMemcpyAsync(b->h_result + (size_t)t * kResultSub, src, sizeof(DevResultSlot) * kResultSub, cudaMemcpyDeviceToHost, b->result_stream));
+  CK(cudaEventRecord(b->result_done[t], b->result_stream));
   *ticket = t;
   return CPBUS_OK;
 }
