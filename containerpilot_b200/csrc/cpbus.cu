@@ -708,6 +708,7 @@ int cpbus_send(cpbus_t* b, uint32_t sub_id, const cpbus_event* ev) {
   if (!b || !ev || ev->code >= CPBUS_N_CODES) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  if (!b->h_active[l]) return CPBUS_ECLOSED;   // the mailbox is gone (Go: send on a closed channel panics)
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = stage_one(b, ev->code, ev->source_id, sub_id, CPBUS_F_UNICAST))) return rc;
   b->st.publishes++;

@@ -226,6 +226,7 @@ def test_unsubscribe_twice_and_unknown_ids():
         assert e.value.status == nat.ENOENT
         assert bus.publish(1, 0) == nat.OK and bus.flush() == nat.OK   # publishing to nobody is fine (jobs_test.go:33-38)
         assert bus.publish(17, 0) == nat.EINVAL
+        assert bus.send(s, 1, 0) == nat.ECLOSED and bus.send(99, 1, 0) == nat.ENOENT     # direct send to a mailbox that is gone
         assert bus.advance(5) == nat.OK and bus.advance(4) == nat.EORDER
 
 
