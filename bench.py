@@ -464,6 +464,15 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(min(n_subs, 65_536))
 
+    if world > 1:
+        # importers unmap the publisher's stream before the publisher frees it
+        torch.cuda.synchronize()
+        if peer_trace is not None:
+            try:
+                bus.shared_close(peer_trace)
+            except Exception as ex:                                    # pragma: no cover - teardown only
+                print(f"[bench] peer unmap: {ex!r}", file=sys.stderr)
+        dist.barrier()
     bus.close()
     if rank == 0:
         line = {
