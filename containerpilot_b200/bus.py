@@ -74,6 +74,14 @@ class Bus:
         nat.check(self._lib.cpbus_subscribe_many(self._h, m.ctypes.data, m.size, C.byref(out)), "cpbus_subscribe_many")
         return out.value
 
+    def subscribe_pairs(self, mask: int, pairs) -> int:
+        """second-level filter: `pairs` = exact (code, source_id) cases delivered on top of the code mask"""
+        pr = np.ascontiguousarray([(int(c), int(s)) for c, s in pairs], dtype=np.uint32).reshape(-1, 2)
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_subscribe_pairs(self._h, mask, pr.ctypes.data if len(pr) else None, len(pr), C.byref(out)),
+                  "cpbus_subscribe_pairs")
+        return out.value
+
     def unsubscribe(self, sub_id: int):
         nat.check(self._lib.cpbus_unsubscribe(self._h, sub_id), "cpbus_unsubscribe")
 

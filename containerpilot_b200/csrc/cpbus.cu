@@ -101,6 +101,9 @@ struct cpbus {
   // registry mirror (events/bus.go:13 `registry map[*Subscriber]bool`)
   std::vector<uint32_t> h_mask;
   std::vector<uint8_t> h_active;
+  std::vector<uint8_t> h_npairs;          // second-level filter: exact {code, source} cases per subscriber (empty until first use)
+  uint2* d_pairs = nullptr;               // N x CPBUS_MAX_PAIRS, allocated by the first cpbus_subscribe_pairs
+  uint32_t n_paired = 0;                  // active subscribers with a pair table
   uint32_t* d_order = nullptr;            // active subscribers sorted by code mask (ORDERED fan-out)
   uint32_t n_order = 0, n_filtered = 0;   // n_filtered: active subscribers whose mask is not CPBUS_MASK_ALL
   bool order_dirty = true, use_order = true;
@@ -140,7 +143,8 @@ uint32_t mask_word(const cpbus* b, uint32_t local) {
     for (uint32_t k = 0; k < b->K; k++)
       if (b->h_timers[(size_t)local * b->K + k].active) hint = k + 1;
   if (!b->h_active[local]) return 0;
-  return (b->h_mask[local] & CPBUS_MASK_ALL) | (hint << kTimerHintShift) | kActiveBit;
+  const uint32_t pair_bit = (!b->h_npairs.empty() && b->h_npairs[local]) ? kPairBit : 0u;
+  return (b->h_mask[local] & CPBUS_MASK_ALL) | (hint << kTimerHintShift) | pair_bit | kActiveBit;
 }
 
 void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
@@ -165,12 +169,12 @@ int rebuild_order(cpbus* b) {
   return CPBUS_OK;
 }
 
-template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED>
+template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED, bool PAIRS = false>
 int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem) {
   static bool attr_done[64] = {};   // per instantiation AND per device: function attributes are per-device state
   const int dev = b->device & 63;
   if (!attr_done[dev]) {
-    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST, ORDERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(fanout_kernel<STORE, TIMERS, DIGEST, ORDERED, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done[dev] = true;
   }
   if (!grid) {
@@ -196,7 +200,7 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: the next fan-out's prologue overlaps this one's tail
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = b->pdl ? 1 : 0;
-  CK(cudaLaunchKernelEx(&cfg, fanout_kernel<STORE, TIMERS, DIGEST, ORDERED>, p));
+  CK(cudaLaunchKernelEx(&cfg, fanout_kernel<STORE, TIMERS, DIGEST, ORDERED, PAIRS>, p));
   CK(cudaGetLastError());
   return CPBUS_OK;
 }
@@ -229,7 +233,11 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   int rc;
   // ORDERED build (no timers armed, at least one filtered subscriber): walk the mailboxes in code-mask order so that
   // equal masks are neighbours and share one filter pass (cost ~ deliveries + distinct masks, not subscribers x events)
-  if (!p.timers_on && b->use_order && b->n_filtered > 0) {
+  // PAIRS build (some subscriber has exact {code, source} cases): the timers build with the second-level test in its
+  // general path; subscribers without a pair table take the same paths as before
+  const bool pairs_on = b->n_paired > 0 && b->d_pairs;
+  p.pairs = pairs_on ? b->d_pairs : nullptr;
+  if (!pairs_on && !p.timers_on && b->use_order && b->n_filtered > 0) {
     if (b->order_dirty) { const int rc_order = rebuild_order(b); if (rc_order) return rc_order; }
     if (b->n_order) {
       const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
@@ -239,7 +247,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
       grid = std::max(1u, (warps + kWarpsPerCta - 1) / kWarpsPerCta);
     }
   }
-  const int variant = (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0) | (p.order ? 4 : 0);
+  const int variant = pairs_on ? (p.use_digest ? 7 : 6) : (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0) | (p.order ? 4 : 0);
 #define CPBUS_DISPATCH(ST)                                                                \
   switch (variant) {                                                                     \
     case 0: rc = launch_fanout_t<ST, false, false, false>(b, p, grid, smem); break;      \
@@ -247,7 +255,9 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
     case 2: rc = launch_fanout_t<ST, true, false, false>(b, p, grid, smem); break;       \
     case 3: rc = launch_fanout_t<ST, true, true, false>(b, p, grid, smem); break;        \
     case 4: rc = launch_fanout_t<ST, false, false, true>(b, p, grid, smem); break;       \
-    default: rc = launch_fanout_t<ST, false, true, true>(b, p, grid, smem); break;       \
+    case 5: rc = launch_fanout_t<ST, false, true, true>(b, p, grid, smem); break;        \
+    case 6: rc = launch_fanout_t<ST, true, false, false, true>(b, p, grid, smem); break; \
+    default: rc = launch_fanout_t<ST, true, true, false, true>(b, p, grid, smem); break; \
   }
   switch (b->store) {
     case CPBUS_STORE_V4: CPBUS_DISPATCH(CPBUS_STORE_V4); break;
@@ -268,7 +278,8 @@ int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) 
   CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, sizeof(unsigned long long), b->stream));
   const uint32_t threads = 256, grid = (b->n_next + threads - 1) / threads;
   admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_ctl, b->d_timers, b->n_next, b->R, b->K,
-                                                b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats);
+                                                b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats,
+                                                b->n_paired > 0 ? b->d_pairs : nullptr);
   CK(cudaGetLastError());
   b->st.kernel_launches++;
   CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, sizeof(unsigned long long),
@@ -414,7 +425,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   const uint32_t R = cfg->ring_cap ? cfg->ring_cap : 1024;
   const uint32_t B = cfg->batch_cap ? cfg->batch_cap : std::min(256u, R / 2);
   const uint32_t K = cfg->timers_per_sub;
-  if (!cfg->n_max_subs || !is_pow2(R) || R < 64 || B == 0 || B > R / 2 || (B % 32) != 0 || B > 2048) return CPBUS_EINVAL;
+  if (!cfg->n_max_subs || !is_pow2(R) || R < 64 || B == 0 || B > R / 2 || (B % 32) != 0 || B > 1024) return CPBUS_EINVAL;   // 1024: the kernel keeps one match word per 32-event chunk in a lane
   if (!(K == 0 || K == 1 || K == 2 || K == 4 || K == 8)) return CPBUS_EINVAL;
   if (cfg->store_path > CPBUS_STORE_BULK) return CPBUS_EINVAL;
   int ndev = 0;
@@ -507,7 +518,7 @@ int cpbus_destroy(cpbus_t* b) {
   if (!b) return CPBUS_EINVAL;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->d_ring); cudaFree(b->d_ctl); cudaFree(b->d_order);
+  cudaFree(b->d_ring); cudaFree(b->d_ctl); cudaFree(b->d_order); cudaFree(b->d_pairs);
   cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
   if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
   if (b->result_stream) { cudaStreamSynchronize(b->result_stream); cudaStreamDestroy(b->result_stream); }
@@ -579,6 +590,38 @@ int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t
 
 int cpbus_subscribe(cpbus_t* b, uint32_t mask, uint32_t* sub_id) { return cpbus_subscribe_many(b, &mask, 1, sub_id); }
 
+static int push_mask_words(cpbus* b, uint32_t first, uint32_t n);
+
+int cpbus_subscribe_pairs(cpbus_t* b, uint32_t mask, const cpbus_pair* pairs, uint32_t n_pairs, uint32_t* sub_id) {
+  if (!b || n_pairs > CPBUS_MAX_PAIRS || (n_pairs && !pairs)) return CPBUS_EINVAL;
+  for (uint32_t j = 0; j < n_pairs; j++) if (pairs[j].code >= CPBUS_N_CODES) return CPBUS_EINVAL;
+  // a pair whose code is already in the mask adds nothing; what is left decides whether a table is needed at all
+  uint2 row[CPBUS_MAX_PAIRS];
+  uint32_t used = 0;
+  for (uint32_t j = 0; j < n_pairs; j++)
+    if (!((mask >> pairs[j].code) & 1u)) row[used++] = make_uint2(pairs[j].code, pairs[j].source_id);
+  if (used == 0) return cpbus_subscribe_many(b, &mask, 1, sub_id);
+  int rc = dev_guard(b); if (rc) return rc;
+  if (!b->d_pairs) {
+    if (cudaMalloc((void**)&b->d_pairs, (size_t)b->N * CPBUS_MAX_PAIRS * sizeof(uint2)) != cudaSuccess) {
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(pair tables) failed");
+      return CPBUS_ENOMEM;
+    }
+    CK(cudaMemsetAsync(b->d_pairs, 0xFF, (size_t)b->N * CPBUS_MAX_PAIRS * sizeof(uint2), b->stream));   // every slot unused
+    b->h_npairs.assign(b->N, 0);
+  }
+  uint32_t id = 0;
+  if ((rc = cpbus_subscribe_many(b, &mask, 1, &id))) return rc;
+  const uint32_t l = id - b->cfg.sub_id_base;
+  for (uint32_t j = used; j < CPBUS_MAX_PAIRS; j++) row[j] = make_uint2(kPairNone, kPairNone);
+  CK(cudaMemcpyAsync(b->d_pairs + (size_t)l * CPBUS_MAX_PAIRS, row, sizeof(row), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));   // `row` is on the stack
+  b->h_npairs[l] = (uint8_t)used; b->n_paired++;
+  if ((rc = push_mask_words(b, l, 1))) return rc;
+  if (sub_id) *sub_id = id;
+  return CPBUS_OK;
+}
+
 int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   if (!b) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
@@ -589,6 +632,7 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   if (!b->h_active[l]) return CPBUS_ECLOSED;
   b->h_active[l] = 0;
   if (b->h_mask[l] != CPBUS_MASK_ALL) b->n_filtered--;
+  if (!b->h_npairs.empty() && b->h_npairs[l]) { b->h_npairs[l] = 0; b->n_paired--; }
   b->order_dirty = true;
   const uint32_t word = 0;
   CK(cudaMemcpyAsync(&b->d_ctl[l].mask, &word, 4, cudaMemcpyHostToDevice, b->stream));

@@ -29,6 +29,8 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
+constexpr uint32_t kPairBit = 0x10000000u;     // mask word bit 28: subscriber has a {code, source} pair table
+constexpr uint32_t kPairNone = 0xFFFFFFFFu;    // code of an unused pair slot
 constexpr uint64_t kDigestP = 0x9E3779B97F4A7C15ull;
 constexpr uint32_t kPowTableLen = 2048 + 65 + 7;   // batch_cap <= 2048
 
@@ -93,6 +95,7 @@ struct FanoutParams {
   uint32_t use_digest, lossless, timers_on;
   uint32_t smem_cap;          // n_ev rounded up to 32 (shared-memory carve-up)
   uint32_t hints;             // bit0: keep control blocks / timer slots in L2 (evict_last)
+  const uint2* pairs;         // PAIRS build: [n_subs][CPBUS_MAX_PAIRS] exact {code, source_id} cases (unused slot: code = kPairNone)
 };
 
 // ---------------------------------------------------------------- helpers ---
@@ -242,7 +245,9 @@ __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
 // ORDERED (no-timer build only): warps walk the subscribers in code-mask order, so a run of mailboxes with the same
 // mask shares one match/compaction pass and one digest polynomial — filtered fan-out then costs one copy per mailbox
 // plus one filter pass per DISTINCT mask in the warp's block, instead of a filter pass per mailbox.
-template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED>
+// PAIRS (second-level filter, jobs/jobs.go:188-231): a subscriber whose mask word carries kPairBit also takes the broadcast
+// events that equal one of its exact {code, source} cases.  Such mailboxes go through the general two-pass path.
+template <int STORE, bool TIMERS, bool DIGEST, bool ORDERED, bool PAIRS = false>
 __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(const FanoutParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t cap = p.smem_cap;
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       }
       if (DIGEST) dsum = warp_sum64(dsum);
       __syncwarp();
-    } else if (!has_unicast && n_ticks == 0) {
+    } else if (!(PAIRS && (m & kPairBit)) && !has_unicast && n_ticks == 0) {
       if constexpr (!TIMERS) {
         // ================= filtered run: compact the matching event indices, then an output-centric copy =================
         // pass 1: ballot 32 events at a time; matching lanes append their event index to the warp's scratch list
@@ -605,13 +610,31 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     } else {
       // ================= general run: filter + unicast + interleaved ticks, two passes =================
       const uint32_t nchunks = (n + 31) >> 5;
+      // second-level filter: lane j < CPBUS_MAX_PAIRS holds this subscriber's j-th exact {code, source} case
+      uint2 my_pair = make_uint2(kPairNone, 0u);
+      uint32_t n_pairs = 0, pair_codes = 0;
+      if (PAIRS && (m & kPairBit)) {
+        if (lane < CPBUS_MAX_PAIRS) my_pair = __ldg(p.pairs + (size_t)s * CPBUS_MAX_PAIRS + lane);
+        const bool used = my_pair.x < 32u;                       // the host packs used slots first
+        n_pairs = __popc(__ballot_sync(0xffffffffu, used));
+        pair_codes = __reduce_or_sync(0xffffffffu, used ? (1u << my_pair.x) : 0u);
+      }
       uint32_t myword = 0;   // pass A: match bitmap, lane c keeps the ballot of chunk c
       for (uint32_t c = 0; c < nchunks; c++) {
         const uint32_t i = c * 32 + lane;
-        bool match = false;
+        bool match = false, cand = false;
         if (i < n) {
           const uint2 mt = s_meta[i];
           match = (mt.y == CPBUS_TARGET_ALL) ? ((m & mt.x) != 0) : (mt.y == gid);
+          if (PAIRS) cand = !match && mt.y == CPBUS_TARGET_ALL && (mt.x & pair_codes) != 0;
+        }
+        if (PAIRS && n_pairs && __any_sync(0xffffffffu, cand)) {
+          uint32_t ev_code = kPairNone - 1u, ev_src = 0;          // never equals a pair
+          if (cand) { ev_code = s_batch[i].code; ev_src = s_batch[i].source_id; }
+          for (uint32_t j = 0; j < n_pairs; j++) {
+            const uint32_t pc = __shfl_sync(0xffffffffu, my_pair.x, j), ps = __shfl_sync(0xffffffffu, my_pair.y, j);
+            match = match || (ev_code == pc && ev_src == ps);
+          }
         }
         const uint32_t w = __ballot_sync(0xffffffffu, match);
         if ((uint32_t)lane == c) myword = w;
@@ -725,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
 // the batch would append and flag any that lacks the room.  Thread per subscriber.
 __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w_now, const SubCtl* ctl,
                              const DevTimer* timers, uint32_t n_subs, uint32_t ring_cap, uint32_t K, uint32_t sub_base,
-                             uint32_t timers_on, DevStats* stats) {
+                             uint32_t timers_on, DevStats* stats, const uint2* pairs) {
   __shared__ uint32_t hist[32];
   __shared__ uint32_t s_uni;
   if (threadIdx.x < 32) hist[threadIdx.x] = 0;
@@ -744,6 +767,19 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
   if (!(m & kActiveBit)) return;
   uint64_t k = 0;
   for (uint32_t c = 0; c < CPBUS_N_CODES; c++) if ((m >> c) & 1u) k += hist[c];
+  if (pairs && (m & kPairBit)) {   // second-level filter: broadcast events outside the mask that equal an exact {code, source} case
+    const uint2* my = pairs + (size_t)s * CPBUS_MAX_PAIRS;
+    for (uint32_t i = 0; i < n_ev; i++) {
+      const uint32_t code = batch[i].code;
+      if (batch[i].target != CPBUS_TARGET_ALL || code >= CPBUS_N_CODES || ((m >> code) & 1u)) continue;
+      const uint32_t src = batch[i].source_id;
+      for (uint32_t j = 0; j < CPBUS_MAX_PAIRS; j++) {
+        const uint2 pr = my[j];
+        if (pr.x == kPairNone) break;
+        if (pr.x == code && pr.y == src) { k++; break; }
+      }
+    }
+  }
   if (s_uni) {
     const uint32_t gid = sub_base + s;
     for (uint32_t i = 0; i < n_ev; i++) if (batch[i].target == gid) k++;

@@ -132,6 +132,7 @@ class Subscriber : public EventSubscriber {   // events/subscriber.go:13-37
   ChanPtr Rx;
   EventBus* Bus = nullptr;
   void Subscribe(EventBus* bus) override;
+  void Subscribe(EventBus* bus, uint32_t mask, const std::vector<Event>& cases);   // filtered (masks + exact cases)
   void Unsubscribe() override;
   void Receive(const Event& e) override;
   void Wait();
@@ -197,12 +198,17 @@ class EventBus {   // events/bus.go:12-22
   void Register(EventPublisher*) { std::lock_guard<std::recursive_mutex> l(lock_); done_.Add(1); }   // bus.go:91-95
   void Unregister(EventPublisher*) { std::lock_guard<std::recursive_mutex> l(lock_); done_.Done(); }  // bus.go:98-102
 
-  void Subscribe(EventSubscriber* subscriber) {   // bus.go:105-111
+  void Subscribe(EventSubscriber* subscriber) { Subscribe(subscriber, CPBUS_MASK_ALL, {}); }   // bus.go:105-111
+  // The consumer's switch pushed down: `mask` = codes taken whatever the source, `cases` = the exact Event values of its
+  // `switch event { case events.Event{Code, Source}: ... }` (jobs/jobs.go:197-231), at most CPBUS_MAX_PAIRS.
+  void Subscribe(EventSubscriber* subscriber, uint32_t mask, const std::vector<Event>& cases) {
     std::lock_guard<std::recursive_mutex> l(lock_);
     auto* sub = dynamic_cast<Subscriber*>(subscriber);
     if (!sub) throw Panic("interface conversion: EventSubscriber is not *Subscriber");   // bus.go:108
     uint32_t id = 0;
-    Check(cpbus_subscribe(h_, CPBUS_MASK_ALL, &id), "cpbus_subscribe");
+    std::vector<cpbus_pair> pairs;
+    for (const Event& e : cases) pairs.push_back(cpbus_pair{(uint32_t)e.Code, Intern(e.Source)});
+    Check(cpbus_subscribe_pairs(h_, mask, pairs.data(), (uint32_t)pairs.size(), &id), "cpbus_subscribe_pairs");
     sub->id_ = id;
     registry_[sub] = id;
     done_.Add(1);
@@ -370,6 +376,7 @@ class EventBus {   // events/bus.go:12-22
 };
 
 inline void Subscriber::Subscribe(EventBus* bus) { Bus = bus; bus->Subscribe(this); }   // subscriber.go:19-22
+inline void Subscriber::Subscribe(EventBus* bus, uint32_t mask, const std::vector<Event>& cases) { Bus = bus; bus->Subscribe(this, mask, cases); }
 inline void Subscriber::Unsubscribe() { Bus->Unsubscribe(this); }                       // subscriber.go:25-27
 inline void Subscriber::Wait() { Bus->Wait(); }                                         // subscriber.go:35-37
 inline void Subscriber::Receive(const Event& e) {                                       // subscriber.go:30-32: `sub.Rx <- event`

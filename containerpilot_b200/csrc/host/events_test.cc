@@ -232,6 +232,33 @@ static void TestManySubscribers() {
   EXPECT(bus.Wait() == false);
 }
 
+// a Job-shaped consumer subscribes with the exact cases of its switch (jobs/jobs.go:197-231)
+static void TestSubscribeWithCases() {
+  std::printf("TestSubscribeWithCases\n");
+  EventBus bus(EventBus::Clock::Virtual, 16);
+  Subscriber job, all;
+  job.Rx = MakeChan(1000); all.Rx = MakeChan(1000);
+  const std::vector<Event> cases{{ExitSuccess, "check.web"}, {ExitFailed, "check.web"}, {Quit, "web"}, GlobalShutdown,
+                                 {Signal, "SIGHUP"}, {StatusHealthy, "watch.db"}};
+  job.Subscribe(&bus, 0u, cases);
+  all.Subscribe(&bus);
+  const std::vector<Event> stream{{ExitSuccess, "check.web"}, {ExitSuccess, "check.api"}, {StatusHealthy, "watch.db"},
+                                  {StatusHealthy, "watch.cache"}, {Metric, "m|1"}, {Signal, "SIGHUP"}, {Signal, "SIGTERM"},
+                                  {Quit, "web"}, {Quit, "api"}, GlobalShutdown};
+  std::vector<Event> want;
+  for (auto& e : stream) {
+    bus.Publish(e);
+    if (std::find(cases.begin(), cases.end(), e) != cases.end()) want.push_back(e);
+  }
+  std::vector<Event> got, got_all; Event e;
+  while (job.Rx->Recv(&e)) got.push_back(e);
+  while (all.Rx->Recv(&e)) got_all.push_back(e);
+  EXPECT(got == want);
+  EXPECT(got_all == stream);
+  job.Unsubscribe(); all.Unsubscribe();
+  EXPECT(bus.Wait() == false);
+}
+
 int main() {
   TestNames();
   TestPubSubInterfaces();
@@ -242,6 +269,7 @@ int main() {
   TestTimers();
   TestConfig1Plumbing();
   TestManySubscribers();
+  TestSubscribeWithCases();
   std::printf(failures ? "FAILED (%d)\n" : "PASS\n", failures);
   return failures ? 1 : 0;
 }

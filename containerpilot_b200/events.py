@@ -120,10 +120,14 @@ class EventBus:
         if self._done < 0:
             raise BusPanic("sync: negative WaitGroup counter")
 
-    def Subscribe(self, subscriber, mask: int = nat.MASK_ALL):   # bus.go:105-111
+    def Subscribe(self, subscriber, mask: int = nat.MASK_ALL, cases=None):   # bus.go:105-111
+        """`cases`: exact Event values of the consumer's switch (jobs/jobs.go:197-231) delivered on top of `mask`"""
         if not isinstance(subscriber, Subscriber):
             raise BusPanic("interface conversion: EventSubscriber is not *Subscriber")
-        subscriber._id = self._bus.subscribe(mask)
+        if cases:
+            subscriber._id = self._bus.subscribe_pairs(mask, [(e.Code, self._bus.intern(e.Source)) for e in cases])
+        else:
+            subscriber._id = self._bus.subscribe(mask)
         self._subs[subscriber] = subscriber._id
         self._done += 1
 
@@ -231,11 +235,11 @@ class Subscriber:
     def __eq__(self, other):
         return self is other
 
-    def Subscribe(self, bus: EventBus, mask: int = nat.MASK_ALL):
+    def Subscribe(self, bus: EventBus, mask: int = nat.MASK_ALL, cases=None):
         self.Bus = bus
         if self.Rx is not None:
             self.Rx._sub = self
-        bus.Subscribe(self, mask)
+        bus.Subscribe(self, mask, cases)
 
     def Unsubscribe(self):
         self.Bus.Unsubscribe(self)

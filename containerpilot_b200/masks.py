@@ -8,9 +8,12 @@ so a mask has to cover EVERY code a consumer can react to:
   Metric  telemetry/metrics.go:92-106
   Watch   not a bus subscriber (private rx + its own timer, watches/watches.go:65-100)
 
-Source matching (`{ExitSuccess, "check.myjob"}` vs any other ExitSuccess) stays in the consumer:
-the mask is a superset filter on the code only.  Timer ticks and direct sends are unicast and
-bypass the mask, exactly like a direct channel write.
+Source matching (`{ExitSuccess, "check.myjob"}` vs any other ExitSuccess): the mask is a superset
+filter on the code only.  Every case of these switches compares a whole Event value, so the exact
+filter is a short list of {code, source} cases (row N3): `JobSwitch.cases()` / `MetricSwitch.cases()`
+feed `EventBus.Subscribe(sub, mask, cases)` -> `cpbus_subscribe_pairs`, and the mailbox then holds
+only what the consumer handles.  Timer ticks and direct sends are unicast and bypass both levels,
+exactly like a direct channel write.
 """
 from __future__ import annotations
 
@@ -66,6 +69,26 @@ class JobSwitch:
     def mask(self) -> int:
         return job_mask(self.start_event.Code, self.stopping_wait_event.Code if self.stopping_wait_event else None)
 
+    def cases(self) -> tuple[int, list]:
+        """(mask, cases) for the exact second-level filter: every case of the switch as a whole Event value (at most
+        16 = CPBUS_MAX_PAIRS).  The three TimerExpired cases normally arrive unicast; they are listed so that a
+        broadcast one would still be delivered, like the switch would match it."""
+        n = self.name
+        cs = [ev.Event(ev.TimerExpired, f"{n}.heartbeat"), ev.Event(ev.TimerExpired, f"{n}.run-every"),
+              ev.Event(ev.TimerExpired, f"{n}.wait-timeout"),
+              ev.Event(ev.ExitFailed, self.health), ev.Event(ev.ExitSuccess, self.health),
+              ev.Event(ev.Quit, n), ev.GlobalShutdown, ev.QuitByTest,
+              ev.GlobalEnterMaintenance, ev.GlobalExitMaintenance,
+              ev.Event(ev.ExitSuccess, n), ev.Event(ev.ExitFailed, n),
+              ev.Event(ev.Signal, "SIGHUP"), ev.Event(ev.Signal, "SIGUSR2"), self.start_event]
+        if self.stopping_wait_event is not None:
+            cs.append(self.stopping_wait_event)
+        out = []
+        for c in cs:
+            if c not in out:
+                out.append(c)
+        return 0, out
+
     def handles(self, e: ev.Event) -> bool:
         n = self.name
         return (e in (ev.Event(ev.TimerExpired, f"{n}.heartbeat"), ev.Event(ev.TimerExpired, f"{n}.run-every"),
@@ -81,6 +104,9 @@ class JobSwitch:
 class MetricSwitch:
     def mask(self) -> int:
         return METRIC_MASK
+
+    def cases(self) -> tuple[int, list]:
+        return 1 << ev.Metric, [ev.GlobalShutdown, ev.QuitByTest]     # any Metric source; the two exact stop events
 
     def handles(self, e: ev.Event) -> bool:
         return e.Code == ev.Metric or e in (ev.GlobalShutdown, ev.QuitByTest)

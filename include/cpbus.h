@@ -40,6 +40,10 @@ enum {
  * filter: events/bus.go:134-138 delivers every event to every subscriber). */
 #define CPBUS_MASK_ALL 0x0001FFFFu
 
+/* one exact case of a consumer's event switch: events.Event{Code, Source} (jobs/jobs.go:197-231) */
+typedef struct cpbus_pair { uint32_t code, source_id; } cpbus_pair;
+#define CPBUS_MAX_PAIRS 16
+
 #define CPBUS_TARGET_ALL 0xFFFFFFFFu /* broadcast (EventBus.Publish)            */
 #define CPBUS_F_TICK     0x1u        /* record produced by a timer (events/timer.go) */
 #define CPBUS_F_UNICAST  0x2u        /* direct mailbox send (`sub.Rx <- ev`, jobs/jobs.go:262) */
@@ -87,7 +91,7 @@ enum {
 typedef struct cpbus_config {
   uint32_t n_max_subs;     /* capacity of this shard's subscriber table           */
   uint32_t ring_cap;       /* records per mailbox; power of two, >= 64 (1024 = default; reference channel cap is 1000, jobs/jobs.go:23) */
-  uint32_t batch_cap;      /* max events per flush; <= ring_cap/2, multiple of 32 */
+  uint32_t batch_cap;      /* max events per flush; <= min(ring_cap/2, 1024), multiple of 32 */
   uint32_t timers_per_sub; /* timer slots per subscriber: 0,1,2,4,8               */
   uint32_t flags;          /* CPBUS_CFG_*                                         */
   int32_t  device;         /* CUDA device ordinal; -1 = current device            */
@@ -134,6 +138,12 @@ int cpbus_source(cpbus_t* bus, uint32_t source_id, char* out, size_t cap, size_t
  *      publishes: any staged events are flushed first. ---- */
 int cpbus_subscribe(cpbus_t* bus, uint32_t code_mask, uint32_t* sub_id);
 int cpbus_subscribe_many(cpbus_t* bus, const uint32_t* code_masks, uint32_t n, uint32_t* first_sub_id);
+/* Second-level filter.  A consumer's `switch event { case events.Event{Code, Source}: ... }`
+ * (jobs/jobs.go:188-231) compares whole Event values, so each case is an exact {code, source} pair.  The subscriber
+ * receives a broadcast event when its code is in code_mask (any source) OR {code, source_id} equals one of the
+ * n_pairs <= CPBUS_MAX_PAIRS pairs.  Unicast records and timer ticks bypass both levels, like a direct channel send.
+ * CPBUS_EINVAL: n_pairs > CPBUS_MAX_PAIRS, a pair's code >= CPBUS_N_CODES, or pairs == NULL with n_pairs > 0. */
+int cpbus_subscribe_pairs(cpbus_t* bus, uint32_t code_mask, const cpbus_pair* pairs, uint32_t n_pairs, uint32_t* sub_id);
 int cpbus_unsubscribe(cpbus_t* bus, uint32_t sub_id);
 
 /* ---- timers: NewEventTimer / NewEventTimeout (events/timer.go:40-71 / 12-37).

@@ -57,6 +57,8 @@ typedef struct orc_sub {
   size_t box_cap;
   orc_timer* timers;   /* [timers_per_sub] */
   uint32_t n_active_timers;
+  uint32_t n_pairs;    /* second-level filter: exact {code, source} cases of the consumer's switch */
+  uint32_t pair_code[ORC_MAX_PAIRS], pair_src[ORC_MAX_PAIRS];
 } orc_sub;
 
 struct orc_bus {
@@ -166,6 +168,30 @@ int orc_subscribe(orc_bus* b, uint32_t mask, uint32_t* sub_id) {
   return ORC_OK;
 }
 
+/* A consumer's `switch event { case events.Event{Code, Source}: ... }` (jobs/jobs.go:188-231) compares whole
+ * Event values: every case is an exact {code, source} pair.  A subscriber may push that down as well: a broadcast
+ * event is wanted when its code is in `mask` (any source) OR {code, source_id} is one of the pairs. */
+int orc_subscribe_pairs(orc_bus* b, uint32_t mask, const uint32_t* codes, const uint32_t* sources, uint32_t n_pairs,
+                        uint32_t* sub_id) {
+  if (n_pairs > ORC_MAX_PAIRS || (n_pairs && (!codes || !sources))) return ORC_EINVAL;
+  for (uint32_t j = 0; j < n_pairs; j++) if (codes[j] >= ORC_N_CODES) return ORC_EINVAL;
+  uint32_t id = 0;
+  int r = orc_subscribe(b, mask, &id);
+  if (r) return r;
+  orc_sub* s = &b->subs[id - b->base];
+  s->n_pairs = n_pairs;
+  for (uint32_t j = 0; j < n_pairs; j++) { s->pair_code[j] = codes[j]; s->pair_src[j] = sources[j]; }
+  if (sub_id) *sub_id = id;
+  return ORC_OK;
+}
+
+static int wants(const orc_sub* s, uint32_t code, uint32_t source_id) {
+  if (code < 32 && ((s->mask >> code) & 1u)) return 1;
+  for (uint32_t j = 0; j < s->n_pairs; j++)
+    if (s->pair_code[j] == code && s->pair_src[j] == source_id) return 1;
+  return 0;
+}
+
 /* Unsubscribe — events/bus.go:114-122.  Done() on an already-unsubscribed
  * subscriber drives the WaitGroup negative => Go panics; here ORC_ECLOSED. */
 int orc_unsubscribe(orc_bus* b, uint32_t gid) {
@@ -190,13 +216,13 @@ int orc_publish(orc_bus* b, uint32_t code, uint32_t source_id) {
   if (b->cap)
     for (uint32_t i = 0; i < b->n_next; i++) {
       orc_sub* s = &b->subs[i];
-      if (s->active && code < 32 && ((s->mask >> code) & 1u) && mailbox_full(b, s)) return ORC_EAGAIN;
+      if (s->active && wants(s, code, source_id) && mailbox_full(b, s)) return ORC_EAGAIN;
     }
   if (code != ORC_METRIC && code < ORC_N_CODES) b->by_code[code]++;   /* bus.go:130-132 */
   for (uint32_t i = 0; i < b->n_next; i++) {                          /* bus.go:134-138 */
     orc_sub* s = &b->subs[i];
     if (!s->active) continue;
-    if (code < 32 && ((s->mask >> code) & 1u)) receive(b, s, &e);
+    if (wants(s, code, source_id)) receive(b, s, &e);
   }
   enqueue(b, &e);                                                     /* bus.go:139 */
   b->seq++;

@@ -64,6 +64,10 @@ orc_bus* orc_new(uint32_t n_max_subs, uint32_t timers_per_sub, uint32_t keep_win
 void orc_free(orc_bus*);
 
 int orc_subscribe(orc_bus*, uint32_t mask, uint32_t* sub_id);
+/* mask (any source) OR one of up to ORC_MAX_PAIRS exact {code, source_id} pairs (jobs/jobs.go:188-231) */
+#define ORC_MAX_PAIRS 16
+int orc_subscribe_pairs(orc_bus*, uint32_t mask, const uint32_t* codes, const uint32_t* sources, uint32_t n_pairs,
+                        uint32_t* sub_id);
 int orc_unsubscribe(orc_bus*, uint32_t sub_id);
 int orc_register(orc_bus*);
 int orc_unregister(orc_bus*);

@@ -22,7 +22,8 @@ def lib():
         vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
         sig = {
             "orc_new": (vp, [u32, u32, u32, u32, u32]), "orc_free": (None, [vp]),
-            "orc_subscribe": (C.c_int, [vp, u32, C.POINTER(u32)]), "orc_unsubscribe": (C.c_int, [vp, u32]),
+            "orc_subscribe": (C.c_int, [vp, u32, C.POINTER(u32)]),
+            "orc_subscribe_pairs": (C.c_int, [vp, u32, vp, vp, u32, C.POINTER(u32)]), "orc_unsubscribe": (C.c_int, [vp, u32]),
             "orc_register": (C.c_int, [vp]), "orc_unregister": (C.c_int, [vp]), "orc_set_reload": (None, [vp]),
             "orc_wait": (C.c_int, [vp]), "orc_publish": (C.c_int, [vp, u32, u32]),
             "orc_publish_many": (C.c_int, [vp, vp, vp, C.c_size_t, u64]),
@@ -59,9 +60,14 @@ class Oracle:
         except Exception:
             pass
 
-    def subscribe(self, mask=0x1FFFF):
+    def subscribe(self, mask=0x1FFFF, pairs=None):
         out = C.c_uint32()
-        rc = self.l.orc_subscribe(self.h, mask, C.byref(out))
+        if pairs:
+            codes = np.ascontiguousarray([p[0] for p in pairs], dtype=np.uint32)
+            srcs = np.ascontiguousarray([p[1] for p in pairs], dtype=np.uint32)
+            rc = self.l.orc_subscribe_pairs(self.h, mask, codes.ctypes.data, srcs.ctypes.data, len(pairs), C.byref(out))
+        else:
+            rc = self.l.orc_subscribe(self.h, mask, C.byref(out))
         assert rc == 0, rc
         return out.value
 

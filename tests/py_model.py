@@ -16,8 +16,8 @@ class PyBus:
         self.head, self.tail = -1, 0
 
     # events/bus.go:105-111
-    def subscribe(self, mask):
-        self.subs.append({"active": True, "mask": mask, "box": [], "timers": [None] * self.K})
+    def subscribe(self, mask, pairs=()):
+        self.subs.append({"active": True, "mask": mask, "pairs": set(pairs), "box": [], "timers": [None] * self.K})
         return len(self.subs) - 1
 
     # events/bus.go:114-122
@@ -47,11 +47,12 @@ class PyBus:
             out.append(ev)
         return out
 
-    # events/bus.go:125-140 (+ the pushed-down consumer switch as a code mask)
+    # events/bus.go:125-140 (+ the pushed-down consumer switch: a code mask and the switch's exact Event cases,
+    # jobs/jobs.go:188-231)
     def publish(self, code, src):
         rec = (self.seq, self.now, code, src, TARGET_ALL, 0)
         for sub in self.subs:
-            if sub["active"] and (sub["mask"] >> code) & 1:
+            if sub["active"] and ((sub["mask"] >> code) & 1 or (code, src) in sub["pairs"]):
                 sub["box"].append(rec)
         self._enqueue((code, src))
         self.seq += 1

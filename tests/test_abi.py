@@ -95,6 +95,7 @@ def test_create_rejects_bad_configs_before_touching_the_device():
     assert create(ring_cap=32) == nat.EINVAL              # < 64
     assert create(ring_cap=1024, batch_cap=1024) == nat.EINVAL   # > ring_cap / 2
     assert create(ring_cap=1024, batch_cap=100) == nat.EINVAL    # not a multiple of 32
+    assert create(ring_cap=8192, batch_cap=2048) == nat.EINVAL   # > 1024
     assert create(timers_per_sub=3) == nat.EINVAL
     assert create(store_path=9) == nat.EINVAL
     assert lib.cpbus_create(None, None) == nat.EINVAL

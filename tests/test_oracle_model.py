@@ -14,7 +14,7 @@ def run_model(ops, K):
     for op in ops:
         k = op[0]
         if k == "sub":
-            bus.subscribe(op[1])
+            bus.subscribe(op[1], op[2] if len(op) > 2 else ())
         elif k == "unsub":
             bus.unsubscribe(op[1])
         elif k == "pub":
@@ -45,3 +45,31 @@ def test_c_oracle_agrees_with_python_model(seed):
     dbg = [(int(r["code"]), int(r["source_id"])) for r in orc.debug_events()]
     assert dbg == model.debug_events()
     assert orc.total_deliveries() == sum(len(x["box"]) for x in model.subs)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_pair_filter_agrees_with_python_model(seed):
+    """second-level filter (exact {code, source} cases of the consumer switch, jobs/jobs.go:188-231)"""
+    K = (0, 2)[seed % 2]
+    ops, n_total = tr.random_ops(seed + 900, 12, 3000, timers_per_sub=K, max_subs=24, p_filter=0.8, p_send=0.05,
+                                 n_sources=5, p_pairs=0.7)
+    assert any(len(op) > 2 for op in ops if op[0] == "sub")
+    orc = tr.run_oracle(ops, 24, timers_per_sub=K)
+    model = run_model(ops, K)
+    for s in range(n_total):
+        got = [tuple(int(x) for x in r) for r in orc.mailbox(s)]
+        assert got == model.subs[s]["box"], f"seed {seed} subscriber {s}"
+    assert orc.total_deliveries() == sum(len(x["box"]) for x in model.subs)
+
+
+def test_pair_filter_semantics():
+    orc = ob.Oracle(4)
+    a = orc.subscribe(0, pairs=[(2, 7), (3, 9)])          # only {ExitSuccess,7} and {ExitFailed,9}
+    b = orc.subscribe(1 << 2, pairs=[(3, 9)])            # every code-2 event, plus {3,9}
+    c = orc.subscribe(0)                                 # nothing
+    for code, src in [(2, 7), (2, 8), (3, 9), (3, 7), (4, 9)]:
+        assert orc.publish(code, src) == 0
+    assert [(int(r["code"]), int(r["source_id"])) for r in orc.mailbox(a)] == [(2, 7), (3, 9)]
+    assert [(int(r["code"]), int(r["source_id"])) for r in orc.mailbox(b)] == [(2, 7), (2, 8), (3, 9)]
+    assert orc.count(c) == 0
+    assert orc.l.orc_subscribe_pairs(orc.h, 0, None, None, 17, None) == -1          # too many pairs

@@ -42,7 +42,7 @@ def zipf_codes(n: int, s: float, seed: int) -> np.ndarray:
 def random_ops(seed: int, n_subs0: int, n_ops: int, timers_per_sub: int = 0, p_filter: float = 0.5,
                p_send: float = 0.02, p_adv: float = 0.3, p_member: float = 0.01, p_timer: float = 0.02,
                max_subs: int | None = None, n_sources: int = 64, dt_max: int = 5000, period_min: int = 2000,
-               period_max: int = 40000, p_flush: float = 0.01):
+               period_max: int = 40000, p_flush: float = 0.01, p_pairs: float = 0.0):
     """A mixed trace: subscribes/unsubscribes, publishes, direct sends, clock advances, timers."""
     rng = np.random.default_rng(seed)
     max_subs = max_subs or n_subs0 + 16
@@ -55,13 +55,21 @@ def random_ops(seed: int, n_subs0: int, n_ops: int, timers_per_sub: int = 0, p_f
     def new_mask():
         return MASK_ALL if rng.random() > p_filter else int(rng.integers(0, 1 << 17))
 
+    def new_sub():
+        m = new_mask()
+        if p_pairs and rng.random() < p_pairs:   # second-level filter: exact {code, source} cases on top of a narrower mask
+            m &= int(rng.integers(0, 1 << 17))
+            pairs = [(int(rng.integers(0, 17)), int(rng.integers(0, n_sources))) for _ in range(int(rng.integers(1, 17)))]
+            return ("sub", m, pairs)
+        return ("sub", m)
+
     for _ in range(n_subs0):
-        ops.append(("sub", new_mask()))
+        ops.append(new_sub())
         active.append(n_total); n_total += 1
     for _ in range(n_ops):
         r = rng.random()
         if r < p_member and n_total < max_subs:
-            ops.append(("sub", new_mask())); active.append(n_total); n_total += 1
+            ops.append(new_sub()); active.append(n_total); n_total += 1
         elif r < 2 * p_member and len(active) > 1:
             s = active.pop(int(rng.integers(0, len(active))))
             ops.append(("unsub", s))
@@ -102,7 +110,7 @@ def run_oracle(ops, n_max_subs, timers_per_sub=0, keep_window=0, sub_id_base=0, 
     for op in ops:
         k = op[0]
         if k == "sub":
-            orc.subscribe(op[1])
+            orc.subscribe(op[1], op[2] if len(op) > 2 else None)
         elif k == "unsub":
             assert orc.unsubscribe(sub_id_base + op[1]) == 0
         elif k == "pub":
@@ -128,7 +136,10 @@ def run_bus(bus, ops, sub_id_base=0):
     for op in ops:
         k = op[0]
         if k == "sub":
-            bus.subscribe(op[1])
+            if len(op) > 2:
+                bus.subscribe_pairs(op[1], op[2])
+            else:
+                bus.subscribe(op[1])
         elif k == "unsub":
             bus.unsubscribe(sub_id_base + op[1])
         elif k == "pub":
