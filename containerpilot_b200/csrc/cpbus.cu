@@ -227,7 +227,6 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   // (65,536 subscribers, 2-4 MiB: +3 %); at 1,048,576 subscribers (64 MiB with timers) it costs 8 %.
   const size_t hot_bytes = (size_t)b->n_next * (sizeof(SubCtl) + (p.timers_on ? b->K * sizeof(DevTimer) : 0));
   p.hints = b->hints >= 0 ? (uint32_t)b->hints : (hot_bytes <= (16u << 20) ? 1u : 0u);
-  const size_t smem = fanout_smem_bytes(p.smem_cap);
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
@@ -237,6 +236,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   // general path; subscribers without a pair table take the same paths as before
   const bool pairs_on = b->n_paired > 0 && b->d_pairs;
   p.pairs = pairs_on ? b->d_pairs : nullptr;
+  const size_t smem = fanout_smem_bytes(p.smem_cap) + (pairs_on ? kPairFilterBytes : 0);   // + the batch's {code, source} presence filter
   if (!pairs_on && !p.timers_on && b->use_order && b->n_filtered > 0) {
     if (b->order_dirty) { const int rc_order = rebuild_order(b); if (rc_order) return rc_order; }
     if (b->n_order) {

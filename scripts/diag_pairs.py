@@ -1,0 +1,49 @@
+"""What the two filter levels buy on a Job-shaped fleet: the same event stream fanned out to N
+job subscribers with (a) all-ones masks = the reference bus, (b) code masks derived from the job switch (N1),
+(c) the switch's exact {code, source} cases (N3).  Prints deliveries and time per 512-event batch."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from containerpilot_b200 import _native as nat
+from containerpilot_b200 import events as ev
+from containerpilot_b200 import masks
+from containerpilot_b200.bus import Bus, EVENT_DTYPE
+
+N = int(os.environ.get("N_JOBS", 32768)); B = 512; WARM, STEPS = 20, 200
+rng = np.random.default_rng(7)
+# source ids: 0 "", 1 global, 2 closed, 3 SIGHUP, 4 SIGUSR2, then 5 per job: name, check, heartbeat, run-every, wait-timeout
+fixed = {"": 0, "global": 1, "closed": 2, "SIGHUP": 3, "SIGUSR2": 4}
+def sid(name):
+    if name in fixed: return fixed[name]
+    base, _, suffix = name.partition(".")
+    if base == "check": return 5 + 5 * int(suffix[3:]) + 1
+    j = int(base[3:])
+    return 5 + 5 * j + {"": 0, "heartbeat": 2, "run-every": 3, "wait-timeout": 4}[suffix]
+subs = []
+for j in range(N):
+    dep = int(rng.integers(0, N))
+    sw = masks.JobSwitch(f"job{j}", start_event=ev.Event(ev.ExitSuccess, f"job{dep}") if j % 3 else ev.GlobalStartup)
+    m, cases = sw.cases()
+    subs.append((sw.mask(), m, [(e.Code, sid(e.Source)) for e in cases]))
+n_src = 5 + 5 * N
+events = np.zeros((WARM + STEPS) * B, dtype=EVENT_DTYPE)
+events["code"] = rng.integers(1, 17, len(events)); events["source_id"] = rng.integers(0, n_src, len(events))
+for label in ("all-ones (reference)", "N1 code masks", "N3 exact cases"):
+    with Bus(N, ring_cap=1024, batch_cap=B) as bus:
+        t0 = time.perf_counter()
+        if label.startswith("all"): bus.subscribe_many(np.full(N, nat.MASK_ALL, dtype=np.uint32))
+        elif label.startswith("N1"): bus.subscribe_many(np.array([s[0] for s in subs], dtype=np.uint32))
+        else:
+            for _, m, pr in subs: bus.subscribe_pairs(m, pr)
+        t_sub = time.perf_counter() - t0
+        def run(lo, hi):
+            for i in range(lo, hi):
+                nat.check(bus.publish_many(events[i * B:(i + 1) * B]), "publish"); nat.check(bus.flush(), "flush")
+            bus.sync()
+        run(0, WARM)
+        d0 = bus.stats()["deliveries"]
+        t0 = time.perf_counter(); run(WARM, WARM + STEPS); dt = time.perf_counter() - t0
+        d = bus.stats()["deliveries"] - d0
+        print(f"{label:22s} N={N}: {d / STEPS:12.1f} deliveries/batch, {dt / STEPS * 1e6:8.1f} us/batch, "
+              f"{STEPS * B / dt:10.3e} publishes/s  (subscribe: {t_sub:.2f} s)", flush=True)
