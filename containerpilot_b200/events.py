@@ -23,8 +23,10 @@ from __future__ import annotations
 from collections import deque
 from dataclasses import dataclass
 
+import numpy as np
+
 from . import _native as nat
-from .bus import Bus
+from .bus import Bus, EVENT_DTYPE
 
 # EventCode enum — events/events.go:21-39
 (None_, ExitSuccess, ExitFailed, Stopping, Stopped, StatusHealthy, StatusUnhealthy, StatusChanged, TimerExpired,
@@ -156,6 +158,20 @@ class EventBus:
             if sub.Rx is not None and sub.Rx.closed:
                 raise BusPanic("send on closed channel")     # bus.go:135-137
         rc = self._bus.publish(event.Code, self._bus.intern(event.Source))
+        if rc == nat.EAGAIN:
+            raise BlockingIOError("Publish would block: a subscriber mailbox is full")
+        nat.check(rc, "cpbus_publish")
+
+    def PublishMany(self, events):
+        """A burst of Publish calls as one batch (one `cpbus_publish` call, one staging pass): what a fan-in caller such as
+        the /v3/metric handler (control/endpoints.go:125-128) hands over.  Same per-event semantics as Publish."""
+        for sub in self._subs:
+            if sub.Rx is not None and sub.Rx.closed:
+                raise BusPanic("send on closed channel")     # bus.go:135-137
+        batch = np.zeros(len(events), dtype=EVENT_DTYPE)
+        batch["code"] = [e.Code for e in events]
+        batch["source_id"] = [self._bus.intern(e.Source) for e in events]
+        rc = self._bus.publish_many(batch)
         if rc == nat.EAGAIN:
             raise BlockingIOError("Publish would block: a subscriber mailbox is full")
         nat.check(rc, "cpbus_publish")

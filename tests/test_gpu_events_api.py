@@ -156,3 +156,44 @@ def test_cpp_mirror_restates_reference_tests():
     assert os.path.exists(exe), "build with __graft_entry__.build()"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("PASS"), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("body,status,expected", [
+    ("{{\n", 422, {}),
+    ('{"mymetric": 1.0}', 200, {Event(events.Metric, "mymetric|1"): 1}),
+    ('{"mymetric": 1.5, "myothermetric": 2}', 200,
+     {Event(events.Metric, "mymetric|1.5"): 1, Event(events.Metric, "myothermetric|2"): 1}),
+])
+def test_post_metric_as_one_batch(body, status, expected):
+    """control/endpoints_test.go:104-145 through the batched handler (containerpilot_b200/ingest.py)"""
+    from containerpilot_b200 import ingest
+    bus = events.NewEventBus()
+    sensor = events.Subscriber(events.Chan(1000))
+    sensor.Subscribe(bus, 1 << events.Metric)
+    _, got_status = ingest.post_metric(bus, body)
+    assert got_status == status
+    got = Counter(e for e in bus.DebugEvents() if e != events.GlobalStartup)
+    assert dict(got) == expected
+    assert Counter(sensor.Received()) == Counter(expected)
+    sensor.Unsubscribe()
+    bus.close()
+
+
+def test_post_metric_burst_is_one_fan_out():
+    """a 200-key request costs one staging pass and one launch instead of 200 publishes"""
+    import json as _json
+    from containerpilot_b200 import ingest
+    bus = events.NewEventBus(n_max_subs=8, batch_cap=256)
+    subs = [events.Subscriber(events.Chan(1000)) for _ in range(4)]
+    for s in subs:
+        s.Subscribe(bus)
+    body = _json.dumps({f"m{i}": i / 4 for i in range(200)})
+    before = bus._bus.stats()["batches"]
+    assert ingest.post_metric(bus, body) == (None, 200)
+    bus.Flush()
+    assert bus._bus.stats()["batches"] - before == 1
+    want = [Event(events.Metric, f"m{i}|{ingest.go_sprint_v(i / 4)}") for i in range(200)]
+    for s in subs:
+        assert s.Received() == want
+        s.Unsubscribe()
+    bus.close()
