@@ -82,6 +82,23 @@ class Bus:
                   "cpbus_subscribe_pairs")
         return out.value
 
+    def subscribe_pairs_many(self, masks, pairs_per_sub) -> int:
+        """a whole fleet in one call: masks[i] and pairs_per_sub[i] = list of (code, source_id), at most 16 each"""
+        m = np.ascontiguousarray(masks, dtype=np.uint32)
+        n = m.size
+        rows = np.full((n, 16, 2), 0xFFFFFFFF, dtype=np.uint32)
+        cnt = np.zeros(n, dtype=np.uint32)
+        for i, pr in enumerate(pairs_per_sub):
+            if len(pr) > 16:
+                raise nat.CpbusError(nat.EINVAL, "cpbus_subscribe_pairs_many")
+            cnt[i] = len(pr)
+            if len(pr):
+                rows[i, :len(pr)] = np.asarray(pr, dtype=np.uint32).reshape(-1, 2)
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_subscribe_pairs_many(self._h, m.ctypes.data, rows.ctypes.data, cnt.ctypes.data, n, C.byref(out)),
+                  "cpbus_subscribe_pairs_many")
+        return out.value
+
     def unsubscribe(self, sub_id: int):
         nat.check(self._lib.cpbus_unsubscribe(self._h, sub_id), "cpbus_unsubscribe")
 

@@ -622,6 +622,46 @@ int cpbus_subscribe_pairs(cpbus_t* b, uint32_t mask, const cpbus_pair* pairs, ui
   return CPBUS_OK;
 }
 
+int cpbus_subscribe_pairs_many(cpbus_t* b, const uint32_t* masks, const cpbus_pair* pairs, const uint32_t* n_pairs,
+                               uint32_t n, uint32_t* first_sub_id) {
+  if (!b || !n || !masks || !pairs || !n_pairs) return CPBUS_EINVAL;
+  for (uint32_t i = 0; i < n; i++) {
+    if (n_pairs[i] > CPBUS_MAX_PAIRS) return CPBUS_EINVAL;
+    for (uint32_t j = 0; j < n_pairs[i]; j++) if (pairs[(size_t)i * CPBUS_MAX_PAIRS + j].code >= CPBUS_N_CODES) return CPBUS_EINVAL;
+  }
+  if ((uint64_t)b->n_next + n > b->N) return CPBUS_ENOSPC;
+  int rc = dev_guard(b); if (rc) return rc;
+  if (!b->d_pairs) {
+    if (cudaMalloc((void**)&b->d_pairs, (size_t)b->N * CPBUS_MAX_PAIRS * sizeof(uint2)) != cudaSuccess) {
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(pair tables) failed");
+      return CPBUS_ENOMEM;
+    }
+    CK(cudaMemsetAsync(b->d_pairs, 0xFF, (size_t)b->N * CPBUS_MAX_PAIRS * sizeof(uint2), b->stream));   // every slot unused
+    b->h_npairs.assign(b->N, 0);
+  }
+  uint32_t first = 0;
+  if ((rc = cpbus_subscribe_many(b, masks, n, &first))) return rc;
+  const uint32_t l0 = first - b->cfg.sub_id_base;
+  std::vector<uint2> rows((size_t)n * CPBUS_MAX_PAIRS, make_uint2(kPairNone, kPairNone));
+  uint32_t paired = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t m = masks[i] & CPBUS_MASK_ALL;
+    uint32_t used = 0;
+    for (uint32_t j = 0; j < n_pairs[i]; j++) {
+      const cpbus_pair& pr = pairs[(size_t)i * CPBUS_MAX_PAIRS + j];
+      if (!((m >> pr.code) & 1u)) rows[(size_t)i * CPBUS_MAX_PAIRS + used++] = make_uint2(pr.code, pr.source_id);
+    }
+    b->h_npairs[l0 + i] = (uint8_t)used;
+    if (used) paired++;
+  }
+  CK(cudaMemcpyAsync(b->d_pairs + (size_t)l0 * CPBUS_MAX_PAIRS, rows.data(), rows.size() * sizeof(uint2), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->n_paired += paired;
+  if (paired && (rc = push_mask_words(b, l0, n))) return rc;
+  if (first_sub_id) *first_sub_id = first;
+  return CPBUS_OK;
+}
+
 int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   if (!b) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;

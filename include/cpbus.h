@@ -144,6 +144,10 @@ int cpbus_subscribe_many(cpbus_t* bus, const uint32_t* code_masks, uint32_t n, u
  * n_pairs <= CPBUS_MAX_PAIRS pairs.  Unicast records and timer ticks bypass both levels, like a direct channel send.
  * CPBUS_EINVAL: n_pairs > CPBUS_MAX_PAIRS, a pair's code >= CPBUS_N_CODES, or pairs == NULL with n_pairs > 0. */
 int cpbus_subscribe_pairs(cpbus_t* bus, uint32_t code_mask, const cpbus_pair* pairs, uint32_t n_pairs, uint32_t* sub_id);
+/* bulk form for a whole fleet: subscriber i gets code_masks[i] and the first n_pairs[i] (<= CPBUS_MAX_PAIRS) entries of
+ * row i of `pairs` (n rows of CPBUS_MAX_PAIRS entries; the rest of a row is ignored).  One upload instead of n calls. */
+int cpbus_subscribe_pairs_many(cpbus_t* bus, const uint32_t* code_masks, const cpbus_pair* pairs, const uint32_t* n_pairs,
+                               uint32_t n, uint32_t* first_sub_id);
 int cpbus_unsubscribe(cpbus_t* bus, uint32_t sub_id);
 
 /* ---- timers: NewEventTimer / NewEventTimeout (events/timer.go:40-71 / 12-37).

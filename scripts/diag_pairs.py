@@ -35,7 +35,7 @@ for label in ("all-ones (reference)", "N1 code masks", "N3 exact cases"):
         if label.startswith("all"): bus.subscribe_many(np.full(N, nat.MASK_ALL, dtype=np.uint32))
         elif label.startswith("N1"): bus.subscribe_many(np.array([s[0] for s in subs], dtype=np.uint32))
         else:
-            for _, m, pr in subs: bus.subscribe_pairs(m, pr)
+            bus.subscribe_pairs_many([m for _, m, _ in subs], [pr for _, _, pr in subs])
         t_sub = time.perf_counter() - t0
         def run(lo, hi):
             for i in range(lo, hi):

@@ -112,6 +112,34 @@ def test_job_fleet_exact_cases_scaled():
         assert st["deliveries"] < 0.05 * mask_only
 
 
+def test_fleet_registered_in_one_call():
+    """cpbus_subscribe_pairs_many == n calls of cpbus_subscribe_pairs (also mixed with plain subscriptions before and after)"""
+    rng = np.random.default_rng(0xC0DEB2A4)
+    n, n_events = 700, 6000
+    subs = []
+    for i in range(n):
+        m = int(rng.integers(0, 1 << 17)) & int(rng.integers(0, 1 << 17)) if i % 5 else nat.MASK_ALL
+        pr = [(int(rng.integers(0, 17)), int(rng.integers(0, 40))) for _ in range(int(rng.integers(0, 17)))] if i % 7 else []
+        subs.append((m, pr))
+    codes = rng.integers(0, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 40, n_events).astype(np.uint32)
+    orc = ob.Oracle(n + 2, keep_window=1024)
+    orc.subscribe(1 << 3)
+    for m, pr in subs:
+        orc.subscribe(m, pr)
+    orc.subscribe(0, [(4, 4)])
+    orc.publish_many(codes, srcs)
+    with Bus(n + 2, ring_cap=1024, batch_cap=256) as bus:
+        assert bus.subscribe(1 << 3) == 0
+        assert bus.subscribe_pairs_many([m for m, _ in subs], [pr for _, pr in subs]) == 1
+        assert bus.subscribe_pairs(0, [(4, 4)]) == n + 1
+        publish_codes(bus, codes, srcs)
+        nat.check(bus.flush(), "flush"); bus.sync()
+        tr.compare(bus, orc, n + 2)
+        with pytest.raises(nat.CpbusError) as e:
+            bus.subscribe_pairs_many([0], [[(17, 1)]])
+        assert e.value.status == nat.EINVAL
+
+
 def test_pair_filter_lossless_backpressure():
     """admission counts pair matches exactly: a full mailbox of a pair-filtered subscriber stalls the publisher"""
     orc = ob.Oracle(3)
