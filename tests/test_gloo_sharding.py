@@ -28,13 +28,22 @@ def _trace():
     masks = np.where(rng.random(N_TOTAL) < 0.5, 0x1FFFF, rng.integers(0, 1 << 17, N_TOTAL)).astype(np.uint32)
     codes = rng.integers(0, 17, N_EVENTS).astype(np.uint32)
     srcs = rng.integers(0, 4096, N_EVENTS).astype(np.uint32)
+    srcs[::3] = rng.integers(0, 8, len(srcs[::3]))             # a hot set of sources, so that exact {code, source} cases match
     return masks, codes, srcs
+
+
+def _pairs(i):
+    """every third subscriber also pushes down exact {code, source} cases (second-level filter)"""
+    if i % 3:
+        return None
+    rng = np.random.default_rng(1000 + i)
+    return [(int(rng.integers(0, 17)), int(rng.integers(0, 8))) for _ in range(int(rng.integers(1, 9)))]
 
 
 def _run_shard(first, count, masks, codes, srcs):
     orc = ob.Oracle(max(count, 1), timers_per_sub=1, keep_window=64, sub_id_base=first)
     for i in range(count):
-        orc.subscribe(int(masks[first + i]))
+        orc.subscribe(int(masks[first + i]), _pairs(first + i))
         orc.timer_add(first + i, PERIOD, 9000 + first + i, False)
     assert orc.publish_many(codes, srcs, dt_ns=DT) == 0
     return np.array([[orc.count(first + i), orc.digest(first + i)] for i in range(count)], dtype=np.uint64).reshape(count, 2)
