@@ -73,3 +73,33 @@ def test_pair_filter_semantics():
     assert [(int(r["code"]), int(r["source_id"])) for r in orc.mailbox(b)] == [(2, 7), (2, 8), (3, 9)]
     assert orc.count(c) == 0
     assert orc.l.orc_subscribe_pairs(orc.h, 0, None, None, 17, None) == -1          # too many pairs
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pair_filter_is_sandwiched_between_mask_and_code_superset(seed):
+    """what makes the second level a pure optimisation: for any subscriber, mailbox(mask) is a subsequence of
+    mailbox(mask, pairs), which is a subsequence of mailbox(mask | codes of the pairs) — and the middle one is exactly the
+    events of the outer one whose code is in the mask or whose {code, source} is a listed case."""
+    rng = np.random.default_rng(4000 + seed)
+    n_subs, n_events = 12, 4000
+    subs = []
+    for _ in range(n_subs):
+        m = int(rng.integers(0, 1 << 17)) & int(rng.integers(0, 1 << 17))
+        pr = [(int(rng.integers(0, 17)), int(rng.integers(0, 6))) for _ in range(int(rng.integers(0, 17)))]
+        subs.append((m, pr))
+    codes = rng.integers(0, 17, n_events).astype(np.uint32); srcs = rng.integers(0, 6, n_events).astype(np.uint32)
+    lo, mid, hi = ob.Oracle(n_subs), ob.Oracle(n_subs), ob.Oracle(n_subs)
+    for m, pr in subs:
+        sup = m
+        for c, _ in pr:
+            sup |= 1 << c
+        lo.subscribe(m); mid.subscribe(m, pr); hi.subscribe(sup)
+    for o in (lo, mid, hi):
+        assert o.publish_many(codes, srcs) == 0
+    for s, (m, pr) in enumerate(subs):
+        key = lambda box: [(int(r["seq"]), int(r["code"]), int(r["source_id"])) for r in box]
+        a, b, c = key(lo.mailbox(s)), key(mid.mailbox(s)), key(hi.mailbox(s))
+        want = [r for r in c if (m >> r[1]) & 1 or (r[1], r[2]) in set(pr)]
+        assert b == want
+        it = iter(b)
+        assert all(r in it for r in a)          # a is a subsequence of b
