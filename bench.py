@@ -370,6 +370,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "cpbus_dev::fanout_kernel", "alg_bytes_per_launch": alg_bytes,
+                "record_bytes_per_launch": 32.0 * d_local, "state_bytes_per_launch": float(n_subs * per_sub_state + B * 32),
                 "kernel_ms": kernel_ms, "peak_source": peak_src}
 
     # ---- end to end through the public C-ABI with HOST buffers: `e2e` ----
