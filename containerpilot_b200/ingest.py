@@ -79,6 +79,11 @@ def _has_inf(v) -> bool:
     return False
 
 
+def _valid_utf8(s: str) -> str:
+    """an unpaired \\uD800-style escape decodes to U+FFFD in Go (encoding/json decode.go: unquote)"""
+    return s.encode("utf-16", "surrogatepass").decode("utf-16", "replace")
+
+
 def _reject_constant(name):
     raise ValueError(f"invalid JSON literal {name}")         # encoding/json has no NaN / Infinity
 
@@ -87,10 +92,9 @@ def metric_events(body) -> list | None:
     """The events PostMetric would publish for this request body, in document order; None = the body does not decode
     into a map[string]interface{} (the handler answers 422)."""
     if isinstance(body, (bytes, bytearray)):
-        try:
-            body = bytes(body).decode("utf-8")
-        except UnicodeDecodeError:
-            return None
+        # encoding/json replaces invalid UTF-8 inside strings with U+FFFD; outside strings the replacement character is a
+        # syntax error, as the raw bytes are for Go
+        body = bytes(body).decode("utf-8", errors="replace")
     try:
         doc = json.loads(body, parse_constant=_reject_constant)
     except (ValueError, RecursionError):
@@ -102,7 +106,7 @@ def metric_events(body) -> list | None:
     if any(_has_inf(v) for v in doc.values()):               # a number float64 cannot hold: Unmarshal fails in Go
         return None
     try:
-        return [ev.Event(ev.Metric, f"{go_sprint_v(k)}|{go_sprint_v(v)}") for k, v in doc.items()]
+        return [ev.Event(ev.Metric, _valid_utf8(f"{go_sprint_v(k)}|{go_sprint_v(v)}")) for k, v in doc.items()]
     except OverflowError:                                    # same, for integer literals beyond float64
         return None
 

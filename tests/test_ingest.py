@@ -54,3 +54,13 @@ def test_bodies_the_go_decoder_rejects_or_ignores():
     assert bus.batches == []
     assert ingest.post_metric(bus, b'{"a": 1, "a": 2, "b": "x|y"}') == (None, 200)      # duplicate key: last one wins
     assert [(e.Code, e.Source) for e in bus.batches[0]] == [(ev.Metric, "a|2"), (ev.Metric, "b|x|y")]
+
+
+def test_invalid_utf8_and_lone_surrogates_become_replacement_characters():
+    bus = FakeBus()
+    assert ingest.post_metric(bus, b'{"a\xff": "x\xfe"}') == (None, 200)
+    assert ingest.post_metric(bus, '{"s": "\\ud800z", "ok": "\\ud83d\\ude00"}') == (None, 200)
+    got = [e.Source for b in bus.batches for e in b]
+    assert got == ["a\ufffd|x\ufffd", "s|\ufffdz", "ok|\U0001f600"]
+    for src in got:
+        src.encode("utf-8")                                  # internable
