@@ -183,6 +183,7 @@ class EventBus {   // events/bus.go:12-22
     cpbus_config cfg{};
     cfg.n_max_subs = n_max_subs; cfg.ring_cap = mailbox_cap; cfg.batch_cap = mailbox_cap >= 512 ? 256 : mailbox_cap / 2;
     cfg.timers_per_sub = 4; cfg.flags = CPBUS_CFG_LOSSLESS | CPBUS_CFG_DIGEST; cfg.device = -1;
+    batch_cap_ = cfg.batch_cap;
     int rc = cpbus_create(&cfg, &h_);
     if (rc) throw std::runtime_error(std::string("cpbus_create: ") + cpbus_strerror(rc) + " " + cpbus_last_cuda_error());
     start_ = std::chrono::steady_clock::now();
@@ -243,6 +244,28 @@ class EventBus {   // events/bus.go:12-22
       break;
     }
     if (clock_ == Clock::Virtual) { FlushLocked(); DrainAll(false); }
+  }
+  // A burst of Publish calls handed over as batches (one cpbus_publish call and one fan-out per batch_cap events): what a
+  // fan-in caller such as the /v3/metric handler produces (control/endpoints.go:125-128).  Same per-event semantics as
+  // Publish; a full mailbox blocks the batch until the consumers have drained, like a blocked chansend.
+  void PublishMany(const std::vector<Event>& events) {
+    std::lock_guard<std::recursive_mutex> l(lock_);
+    for (auto& kv : registry_)
+      if (kv.first->Rx && kv.first->Rx->Closed()) throw Panic("send on closed channel");   // bus.go:135-137
+    FlushLocked();   // staging buffer empty from here on: a chunk of <= batch_cap_ events never triggers a flush of its own
+    std::vector<cpbus_event> evs;
+    for (size_t i = 0; i < events.size(); i += batch_cap_) {
+      const size_t n = std::min<size_t>(batch_cap_, events.size() - i);
+      evs.assign(n, cpbus_event{});
+      for (size_t j = 0; j < n; j++) {
+        const Event& e = events[i + j];
+        if (String(e.Code) != "Metric") counter_[{String(e.Code), e.Source}]++;            // bus.go:130-132
+        evs[j].code = (uint32_t)e.Code; evs[j].source_id = Intern(e.Source);
+      }
+      Check(cpbus_publish(h_, evs.data(), n), "cpbus_publish");
+      FlushLocked();
+    }
+    if (clock_ == Clock::Virtual) DrainAll(false);
   }
   void PublishSignal(const std::string& sig) { Publish(Event{Signal, sig}); }   // bus.go:144-146
   void SetReloadFlag() { std::lock_guard<std::recursive_mutex> l(lock_); reload_ = true; }   // bus.go:150-154
@@ -368,6 +391,7 @@ class EventBus {   // events/bus.go:12-22
   bool reload_ = false;
   WaitGroup done_;
   std::map<Subscriber*, uint32_t> registry_;   // bus.go:13
+  uint32_t batch_cap_ = 32;                    // events per cpbus_publish batch (PublishMany)
   std::map<std::pair<std::string, std::string>, uint64_t> counter_;   // containerpilot_events{code,source}
   Clock clock_;
   std::chrono::steady_clock::time_point start_;

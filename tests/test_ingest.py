@@ -1,8 +1,13 @@
 """SURVEY §8f N4 — /v3/metric fan-in as one batch (containerpilot_b200/ingest.py).  CPU part: the event construction
 (Go's fmt "%v" on JSON-decoded values, status codes) against the reference's own test vectors
 (control/endpoints_test.go:104-145) and the documented behaviour of fmt / encoding/json."""
+import json
+import os
+import struct
+import subprocess
 from collections import Counter
 
+import numpy as np
 import pytest
 
 from containerpilot_b200 import events as ev
@@ -64,3 +69,74 @@ def test_invalid_utf8_and_lone_surrogates_become_replacement_characters():
     assert got == ["a\ufffd|x\ufffd", "s|\ufffdz", "ok|\U0001f600"]
     for src in got:
         src.encode("utf-8")                                  # internable
+
+
+HOST_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "containerpilot_b200", "csrc", "host")
+
+
+def _cpp_binary():
+    exe = os.path.join(HOST_DIR, "ingest_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", HOST_DIR, "ingest_test"])
+    return exe
+
+
+def test_cpp_mirror_self_test():
+    """containerpilot_b200/csrc/host/ingest.hpp against the same reference vectors (no bus, no GPU)"""
+    out = subprocess.run([_cpp_binary()], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip().endswith("PASS"), out.stdout + out.stderr
+
+
+def test_cpp_and_python_mirrors_agree_on_random_documents():
+    """two independent restatements of json.Unmarshal + fmt %v must produce the same events for the same bodies"""
+    rng = np.random.default_rng(0xC0DEB2A5)
+
+    def rand_float():
+        kind = rng.integers(0, 6)
+        if kind == 0:
+            return float(rng.integers(-10**6, 10**7))
+        if kind == 1:
+            return float(rng.integers(0, 10**6)) / float(10 ** int(rng.integers(0, 9)))
+        if kind == 2:                                           # any finite double, by bit pattern
+            while True:
+                x = struct.unpack("<d", struct.pack("<Q", int(rng.integers(0, 2**63, dtype=np.uint64)) | (int(rng.integers(0, 2)) << 63)))[0]
+                if x == x and abs(x) != float("inf"):
+                    return x
+        if kind == 3:
+            return float(10.0 ** int(rng.integers(-30, 30))) * float(rng.integers(1, 10))
+        if kind == 4:
+            return float(rng.random())
+        return float(rng.integers(0, 100)) / 4
+
+    def rand_value(depth=0):
+        kind = rng.integers(0, 9 if depth < 2 else 6)
+        if kind <= 2:
+            return rand_float()
+        if kind == 3:
+            return ["up", "x|y", "", "h\u00e9llo \u20ac", "tab\there", "\U0001f600"][int(rng.integers(0, 6))]
+        if kind == 4:
+            return [True, False, None][int(rng.integers(0, 3))]
+        if kind == 5:
+            return int(rng.integers(-5, 5))
+        if kind <= 7:
+            return [rand_value(depth + 1) for _ in range(int(rng.integers(0, 4)))]
+        return {f"k{int(rng.integers(0, 5))}": rand_value(depth + 1) for _ in range(int(rng.integers(0, 4)))}
+
+    bodies = []
+    for _ in range(400):
+        doc = {f"metric{int(rng.integers(0, 12))}": rand_value() for _ in range(int(rng.integers(0, 8)))}
+        bodies.append(json.dumps(doc, ensure_ascii=bool(rng.integers(0, 2))))
+    bodies += ["{{", "", "null", "[1]", '{"a": 1e999}', '{"a": 1e-999}', '{"a": -0.0}', '{"a": 1E5, "b": 1e6, "c": 123456.7e1}',
+               '{"a": "\\ud800z"}', '{"dup": 1, "dup": [2]}', '{"a":1,}', '{"n": 12345678901234567890}']
+    assert all("\n" not in b for b in bodies)
+    out = subprocess.run([_cpp_binary(), "--events"], input="\n".join(bodies) + "\n", capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")[:-1]
+    assert len(lines) == len(bodies)
+    n_events = 0
+    for body, line in zip(bodies, lines):
+        evs = ingest.metric_events(body)
+        want = "422" if evs is None else "\t".join(["200"] + [e.Source for e in evs])
+        assert line == want, body
+        n_events += len(evs or [])
+    assert n_events > 1000
