@@ -19,7 +19,9 @@ F_TICK, F_UNICAST = 0x1, 0x2
 CFG_LOSSLESS, CFG_DIGEST = 0x1, 0x2
 STORE_AUTO, STORE_V4, STORE_V8, STORE_BULK = 0, 1, 2, 3
 
-OK, EINVAL, ENOMEM, ECUDA, EAGAIN, ENOSPC, ENOENT, ECLOSED, ENODEV, EORDER = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
+OK, EINVAL, ENOMEM, ECUDA, EAGAIN, ENOSPC, ENOENT, ECLOSED, ENODEV, EORDER, ETIMEDOUT = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
+PUT_STAMP, PUT_RAW = 0, 1
+EPHEMERAL_BIT, EPHEMERAL_SLOTS = 0x80000000, 65536
 
 
 class Event(C.Structure):
@@ -46,7 +48,12 @@ class Stats(C.Structure):
     _fields_ = [("publishes", C.c_uint64), ("deliveries", C.c_uint64), ("ticks", C.c_uint64),
                 ("batches", C.c_uint64), ("kernel_launches", C.c_uint64), ("overwritten", C.c_uint64),
                 ("published_by_code", C.c_uint64 * N_CODES), ("n_subs", C.c_uint32), ("n_timers", C.c_uint32),
-                ("now_ns", C.c_uint64)]
+                ("now_ns", C.c_uint64), ("intern_entries", C.c_uint64), ("intern_bytes", C.c_uint64),
+                ("ephemeral_live", C.c_uint64), ("ephemeral_recycled", C.c_uint64)]
+
+
+class PairCount(C.Structure):
+    _fields_ = [("code", C.c_uint32), ("source_id", C.c_uint32), ("count", C.c_uint64)]
 
 
 assert C.sizeof(Event) == 32
@@ -58,6 +65,7 @@ SYMBOLS = {
     "cpbus_destroy": (C.c_int, [C.c_void_p]),
     "cpbus_intern": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, _P(C.c_uint32)]),
     "cpbus_source": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, _P(C.c_size_t)]),
+    "cpbus_intern_ephemeral": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, _P(C.c_uint32)]),
     "cpbus_subscribe": (C.c_int, [C.c_void_p, C.c_uint32, _P(C.c_uint32)]),
     "cpbus_subscribe_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _P(C.c_uint32)]),
     "cpbus_subscribe_pairs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _P(C.c_uint32)]),
@@ -73,6 +81,14 @@ SYMBOLS = {
     "cpbus_sync": (C.c_int, [C.c_void_p]),
     "cpbus_publish_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),
     "cpbus_publish_device_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "cpbus_stream_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_void_p), C.c_char_p]),
+    "cpbus_stream_open": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, _P(C.c_void_p)]),
+    "cpbus_stream_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _P(C.c_void_p)]),
+    "cpbus_stream_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32]),
+    "cpbus_stream_fanout": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64]),
+    "cpbus_stream_status": (C.c_int, [C.c_void_p]),
+    "cpbus_stream_set_timeout": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "cpbus_stream_close": (C.c_int, [C.c_void_p]),
     "cpbus_shared_alloc": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_void_p), C.c_char_p]),
     "cpbus_shared_open": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_void_p)]),
     "cpbus_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -87,6 +103,7 @@ SYMBOLS = {
     "cpbus_step_result_end": (C.c_int, [C.c_void_p, C.c_uint32, _P(C.c_uint64 * 4)]),
     "cpbus_debug_events": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_stats": (C.c_int, [C.c_void_p, _P(Stats)]),
+    "cpbus_publish_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_device_ptrs": (C.c_int, [C.c_void_p, _P(C.c_void_p), _P(C.c_void_p)]),
     "cpbus_code_name": (C.c_char_p, [C.c_int]),
     "cpbus_code_from_string": (C.c_int, [C.c_char_p]),

@@ -55,6 +55,13 @@ class Bus:
         nat.check(self._lib.cpbus_intern(self._h, raw, len(raw), C.byref(out)), "cpbus_intern")
         return out.value
 
+    def intern_ephemeral(self, s: str) -> int:
+        """payload strings (Metric "key|value"): ids from the bounded, recycled region"""
+        raw = s.encode()
+        out = C.c_uint32()
+        nat.check(self._lib.cpbus_intern_ephemeral(self._h, raw, len(raw), C.byref(out)), "cpbus_intern_ephemeral")
+        return out.value
+
     def source(self, source_id: int) -> str:
         n = C.c_size_t()
         nat.check(self._lib.cpbus_source(self._h, source_id, None, 0, C.byref(n)), "cpbus_source")
@@ -149,6 +156,40 @@ class Bus:
         return self._lib.cpbus_publish_device_staged(self._h, C.c_void_p(dev_ptr), n, watermark_ns,
                                                      C.c_void_p(next_ptr) if next_ptr else None, next_n)
 
+    # -- the publisher's stream across GPUs (one process per GPU) ------------
+    def stream_create(self, n_slots: int, n_consumers: int):
+        """publisher rank: (stream handle, 64-byte IPC handle for the other ranks)"""
+        st, handle = C.c_void_p(), C.create_string_buffer(64)
+        nat.check(self._lib.cpbus_stream_create(self._h, n_slots, n_consumers, C.byref(st), handle), "cpbus_stream_create")
+        return st, handle.raw
+
+    def stream_open(self, handle: bytes, consumer_index: int):
+        st = C.c_void_p()
+        nat.check(self._lib.cpbus_stream_open(self._h, handle, consumer_index, C.byref(st)), "cpbus_stream_open")
+        return st
+
+    def stream_attach(self, owner_stream, consumer_index: int):
+        """same-process consumer of a stream created by another Bus of this process (peer access instead of IPC)"""
+        st = C.c_void_p()
+        nat.check(self._lib.cpbus_stream_attach(self._h, owner_stream, consumer_index, C.byref(st)), "cpbus_stream_attach")
+        return st
+
+    def stream_put(self, st, events: np.ndarray, now_ns: int, raw: bool = False) -> int:
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        return self._lib.cpbus_stream_put(st, ev.ctypes.data if ev.size else None, ev.size, now_ns, nat.PUT_RAW if raw else nat.PUT_STAMP)
+
+    def stream_fanout(self, st, n: int, now_ns: int) -> int:
+        return self._lib.cpbus_stream_fanout(st, n, now_ns)
+
+    def stream_status(self, st) -> int:
+        return self._lib.cpbus_stream_status(st)
+
+    def stream_set_timeout(self, st, microseconds: int):
+        nat.check(self._lib.cpbus_stream_set_timeout(st, microseconds), "cpbus_stream_set_timeout")
+
+    def stream_close(self, st):
+        nat.check(self._lib.cpbus_stream_close(st), "cpbus_stream_close")
+
     def shared_alloc(self, nbytes: int):
         """(device pointer, 64-byte IPC handle) of a new buffer on this bus's GPU, mappable by the other GPUs."""
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -229,6 +270,14 @@ class Bus:
         d = {k: getattr(st, k) for k, _ in nat.Stats._fields_ if k != "published_by_code"}
         d["published_by_code"] = list(st.published_by_code)
         return d
+
+    def publish_counts(self) -> dict:
+        """{(code, source_id): count} — the reference's containerpilot_events{code, source} counter (Metric excluded)"""
+        n = C.c_size_t()
+        nat.check(self._lib.cpbus_publish_counts(self._h, None, 0, C.byref(n)), "cpbus_publish_counts")
+        buf = (nat.PairCount * max(1, n.value))()
+        nat.check(self._lib.cpbus_publish_counts(self._h, buf, n.value, C.byref(n)), "cpbus_publish_counts")
+        return {(buf[i].code, buf[i].source_id): buf[i].count for i in range(n.value)}
 
     def device_ptrs(self) -> dict:
         ring, ctl = C.c_void_p(), C.c_void_p()

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
@@ -34,9 +35,14 @@ thread_local char g_cuda_err[256] = "";
     }                                                                                              \
   } while (0)
 
+// debug ring entry awaiting enqueue: a concrete event, or "the broadcast events of device launch `launch`"
+struct DbgItem { bool marker; unsigned long long launch; cpbus_event ev; };
+
 struct HostTimer { bool active = false, oneshot = false; uint64_t period = 0, next_due = 0; uint32_t source_id = 0; };
 
 }  // namespace
+
+struct cpbus_stream;
 
 struct cpbus {
   cpbus_config cfg{};
@@ -64,6 +70,17 @@ struct cpbus {
   unsigned long long pf_seq[kPrefetch] = {};   // ... and which launch wrote it
   int pf_next = 0;
   std::vector<void*> shared_owned, shared_mapped;   // cpbus_shared_alloc / cpbus_shared_open
+  // stream mode (cpbus_stream_*): device-managed prefetch of later stream batches + sticky error word
+  unsigned long long* d_pf_state = nullptr;   // [kStreamPrefetch]: which stream batch sits in d_prefetch[i]
+  cpbus_event* d_pf_buf = nullptr;            // kStreamPrefetch x batch_cap records (one allocation)
+  unsigned int* h_err = nullptr;              // pinned + mapped: kErr* bits written by the fan-out kernel
+  unsigned int* d_err = nullptr;              // device alias of h_err
+  uint32_t stream_spin_us = 0;                // bound of the in-kernel wait for a stream batch (0 = 2 s)
+  // accounting of device-published batches (cpbus_publish_device*, cpbus_stream_fanout): done by the kernel's lead CTA
+  DevPubAcct* d_acct = nullptr;
+  DevPubAcct* h_acct = nullptr;               // pinned staging for cpbus_stats / cpbus_debug_events / cpbus_publish_counts
+  std::deque<DbgItem> dbg_pending;            // debug-ring entries not yet enqueued (events, or markers of device batches)
+  std::unordered_map<uint64_t, uint64_t> pub_pairs;   // host publishes by (code << 32 | source_id), Metric excluded (bus.go:130-132)
   cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
@@ -122,6 +139,14 @@ struct cpbus {
   // intern table (Event.Source string <-> u32)
   std::unordered_map<std::string, uint32_t> intern;
   std::vector<std::string> sources;
+  size_t intern_bytes = 0;
+  // bounded region for payload strings (Metric "key|value"): recycled oldest-first
+  struct EphSlot { std::string s; uint32_t gen = 0; bool live = false; };
+  std::vector<EphSlot> eph;
+  std::unordered_map<std::string, uint32_t> eph_map;
+  uint32_t eph_next = 0;
+  uint64_t eph_live = 0, eph_recycled = 0;
+  std::vector<cpbus_stream*> streams;     // open streams (closed by cpbus_destroy if the caller did not)
 
   cpbus_stats_t st{};
   std::mutex mu;   // drain/stats from a second thread
@@ -147,11 +172,24 @@ uint32_t mask_word(const cpbus* b, uint32_t local) {
   return (b->h_mask[local] & CPBUS_MASK_ALL) | (hint << kTimerHintShift) | pair_bit | kActiveBit;
 }
 
-void dbg_enqueue(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
+void dbg_ring_put(cpbus* b, const cpbus_event& e) {   // events/bus.go:24-31
   b->dbg[(b->dbg_head + 1) % 10] = e;
   int old = b->dbg_head;
   b->dbg_head = (b->dbg_head + 1) % 10;
   if (old != -1 && b->dbg_head == b->dbg_tail) b->dbg_tail = (b->dbg_tail + 1) % 10;
+}
+
+// While the broadcast events of a device-published batch are still unknown to the host (a marker is pending), later
+// enqueues queue up behind it so that the ring keeps the global publish order; cpbus_debug_events resolves them.
+void dbg_enqueue(cpbus* b, const cpbus_event& e) {
+  if (b->dbg_pending.empty()) { dbg_ring_put(b, e); return; }
+  b->dbg_pending.push_back(DbgItem{false, 0ull, e});
+  if (b->dbg_pending.size() > (size_t)kAcctDbgRing) b->dbg_pending.pop_front();
+}
+
+void dbg_mark_device_batch(cpbus* b, unsigned long long launch) {
+  b->dbg_pending.push_back(DbgItem{true, launch, cpbus_event{}});
+  if (b->dbg_pending.size() > (size_t)kAcctDbgRing) b->dbg_pending.pop_front();
 }
 
 int rebuild_order(cpbus* b) {
@@ -206,18 +244,26 @@ int launch_fanout_t(cpbus* b, const FanoutParams& p, uint32_t grid, size_t smem)
 }
 
 // fan out `n` records at d_src with watermark w (all checks done by the caller)
-int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool staged = false,
+struct StreamArgs {   // stream mode (cpbus_stream_fanout): where this batch's header / ack words live
+  const StreamHdr* hdr = nullptr; unsigned long long* ack = nullptr; unsigned long long seq = 0;
+  const StreamHdr* next_hdr = nullptr;
+};
+
+int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, int staged = 0,
                   const cpbus_event* prefetch_src = nullptr, cpbus_event* prefetch_dst = nullptr, uint32_t prefetch_n = 0,
-                  bool batch_dep = false) {
-  if (b->n_next == 0) return CPBUS_OK;
-  if (n == 0 && b->n_timers == 0) return CPBUS_OK;
+                  bool batch_dep = false, bool account = false, const StreamArgs* sa = nullptr) {
+  if (b->n_next == 0 && !sa) return CPBUS_OK;
+  if (n == 0 && b->n_timers == 0 && !sa) return CPBUS_OK;   // (a stream batch is always consumed: its slot must be acknowledged)
   FanoutParams p{};
   p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.launch_seq = ++b->launch_seq;
   p.desc = b->d_desc + (p.launch_seq & 1) * fanout_desc_bytes(2048);   // two descriptor buffers: launch i+1 may write while launch i reads
   p.desc_ready = b->d_desc_ready + (p.launch_seq & 1) * 16; p.w_now = w;
   p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
   p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
-  p.batch_local = b->d_batch_local; p.staged = staged ? 1u : 0u;
+  p.batch_local = b->d_batch_local; p.staged = (uint32_t)staged;
+  p.err_word = b->d_err; p.acct = account ? b->d_acct : nullptr;
+  p.pf_state = b->d_pf_state; p.pf_buf = b->d_pf_buf; p.pf_stride = b->B; p.spin_us = b->stream_spin_us;
+  if (sa) { p.stream_hdr = sa->hdr; p.stream_ack = sa->ack; p.stream_seq = sa->seq; p.stream_next_hdr = sa->next_hdr; }
   p.prefetch_src = prefetch_src; p.prefetch_dst = prefetch_dst; p.prefetch_n = prefetch_n;
   p.batch_dep = batch_dep ? 1u : 0u; p.n_ev = n;
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
@@ -268,6 +314,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bo
   if (rc) return rc;
   b->st.batches++; b->st.kernel_launches++;
   b->last_watermark = w;
+  if (account && n) dbg_mark_device_batch(b, p.launch_seq);
   return CPBUS_OK;
 }
 
@@ -304,13 +351,14 @@ void retire_oneshots(cpbus* b, uint64_t w) {
 
 int flush_staged(cpbus* b, uint64_t w) {
   const uint32_t n = (uint32_t)b->n_staged;
-  if (n == 0 && (b->n_timers == 0 || w == b->last_watermark)) return CPBUS_OK;
+  if (n == 0 && b->n_timers == 0) { b->last_watermark = std::max(b->last_watermark, w); return CPBUS_OK; }   // nothing armed: the watermark follows the clock
+  if (n == 0 && w == b->last_watermark) return CPBUS_OK;
   const int c = b->cur;
   int rc;
   if (b->zero_copy && !b->lossless) {
     // Zero-copy ingest: the pinned staging buffer is mapped into the device address space; CTA 0 of the fan-out pulls the
     // batch over PCIe in its prologue (the staged path) — no H2D op, no stream waits, consecutive fan-outs stay adjacent.
-    rc = launch_fanout(b, b->h_batch[c], n, w, /*staged=*/true);
+    rc = launch_fanout(b, b->h_batch[c], n, w, /*staged=*/1);
     if (rc) return rc;
     if ((c & (cpbus::kEpoch - 1)) == cpbus::kEpoch - 1) CK(cudaEventRecord(b->consumed[c], b->stream));
     b->n_staged = 0;
@@ -371,7 +419,7 @@ bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 
 extern "C" {
 
-uint32_t cpbus_abi_version(void) { return 1; }
+uint32_t cpbus_abi_version(void) { return 2; }
 
 const char* cpbus_last_cuda_error(void) { return g_cuda_err; }
 
@@ -387,6 +435,7 @@ const char* cpbus_strerror(int s) {
     case CPBUS_ECLOSED: return "subscriber already unsubscribed";
     case CPBUS_ENODEV: return "no CUDA device (libcpbus has no CPU fallback)";
     case CPBUS_EORDER: return "clock moved backwards, batch unsorted or timer window exceeded";
+    case CPBUS_ETIMEDOUT: return "stream batch never arrived (publisher stalled or consumer a whole ring behind)";
     default: return "unknown status";
   }
 }
@@ -482,6 +531,14 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
     if (cudaEventCreateWithFlags(&b->consumed[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
   }
   ALLOC(b->d_batch_local, (size_t)B * sizeof(cpbus_event));
+  ALLOC(b->d_pf_buf, (size_t)kStreamPrefetch * B * sizeof(cpbus_event)); ALLOC(b->d_pf_state, 64);
+  ALLOC(b->d_acct, sizeof(DevPubAcct));
+  if (cudaMemsetAsync(b->d_pf_state, 0, 64, b->stream) != cudaSuccess ||
+      cudaMemsetAsync(b->d_acct, 0, sizeof(DevPubAcct), b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (cudaHostAlloc((void**)&b->h_err, 64, cudaHostAllocMapped) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  memset(b->h_err, 0, 64);
+  if (cudaHostGetDevicePointer((void**)&b->d_err, b->h_err, 0) != cudaSuccess) return fail(CPBUS_ECUDA);
+  if (cudaMallocHost((void**)&b->h_acct, offsetof(DevPubAcct, pair_key)) != cudaSuccess) return fail(CPBUS_ENOMEM);
   for (int i = 0; i < cpbus::kPrefetch; i++) ALLOC(b->d_prefetch[i], (size_t)B * sizeof(cpbus_event));
   ALLOC(b->d_result, sizeof(DevResultSlot) * kResultRing * kResultSub);
   if (cudaMemsetAsync(b->d_result, 0, sizeof(DevResultSlot) * kResultRing * kResultSub, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
@@ -518,6 +575,7 @@ int cpbus_destroy(cpbus_t* b) {
   if (!b) return CPBUS_EINVAL;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
+  while (!b->streams.empty()) cpbus_stream_close(b->streams.back());
   cudaFree(b->d_ring); cudaFree(b->d_ctl); cudaFree(b->d_order); cudaFree(b->d_pairs);
   cudaFree(b->d_timers); cudaFree(b->d_stats); cudaFree(b->d_fold); cudaFree(b->d_pow); cudaFree(b->d_desc); cudaFree(b->d_desc_ready);
   if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
@@ -532,7 +590,9 @@ int cpbus_destroy(cpbus_t* b) {
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->launched) cudaEventDestroy(b->launched);
   cudaFree(b->d_drain); cudaFree(b->d_drain_idx);
-  cudaFree(b->d_result); cudaFree(b->d_batch_local);
+  cudaFree(b->d_result); cudaFree(b->d_batch_local); cudaFree(b->d_pf_buf); cudaFree(b->d_pf_state); cudaFree(b->d_acct);
+  if (b->h_err) cudaFreeHost(b->h_err);
+  if (b->h_acct) cudaFreeHost(b->h_acct);
   for (int i = 0; i < cpbus::kPrefetch; i++) cudaFree(b->d_prefetch[i]);
   for (void* p : b->shared_mapped) cudaIpcCloseMemHandle(p);
   for (void* p : b->shared_owned) cudaFree(p);
@@ -552,15 +612,50 @@ int cpbus_intern(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
   auto it = b->intern.find(key);
   if (it != b->intern.end()) { *source_id = it->second; return CPBUS_OK; }
   if (b->sources.size() >= 0xFFFFFFF0u) return CPBUS_ENOSPC;
+  if (b->sources.size() >= CPBUS_EPHEMERAL_BIT) return CPBUS_ENOSPC;   // permanent ids never carry the ephemeral bit
   const uint32_t id = (uint32_t)b->sources.size();
   b->sources.push_back(key);
+  b->intern_bytes += key.size();
   b->intern.emplace(std::move(key), id);
   *source_id = id;
   return CPBUS_OK;
 }
 
+// Bounded region for payload strings (control/endpoints.go:125-126: Source = "key|value" of every posted metric).
+// id = EPHEMERAL_BIT | generation(15) << 16 | slot(16); the slot's previous string is dropped when it is reused.
+int cpbus_intern_ephemeral(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
+  if (!b || (!s && len) || !source_id) return CPBUS_EINVAL;
+  std::string key(s ? s : "", len);
+  auto perm = b->intern.find(key);
+  if (perm != b->intern.end()) { *source_id = perm->second; return CPBUS_OK; }   // already a name: keep one id per string
+  auto it = b->eph_map.find(key);
+  if (it != b->eph_map.end()) {
+    const cpbus::EphSlot& e = b->eph[it->second];
+    *source_id = CPBUS_EPHEMERAL_BIT | ((e.gen & 0x7FFFu) << 16) | it->second;
+    return CPBUS_OK;
+  }
+  if (b->eph.empty()) b->eph.resize(CPBUS_EPHEMERAL_SLOTS);
+  const uint32_t slot = b->eph_next;
+  b->eph_next = (slot + 1) % CPBUS_EPHEMERAL_SLOTS;
+  cpbus::EphSlot& e = b->eph[slot];
+  if (e.live) { b->eph_map.erase(e.s); b->eph_recycled++; } else b->eph_live++;
+  e.gen++; e.live = true; e.s = key;
+  b->eph_map.emplace(std::move(key), slot);
+  *source_id = CPBUS_EPHEMERAL_BIT | ((e.gen & 0x7FFFu) << 16) | slot;
+  return CPBUS_OK;
+}
+
 int cpbus_source(cpbus_t* b, uint32_t id, char* out, size_t cap, size_t* len) {
-  if (!b || id >= b->sources.size()) return b ? CPBUS_ENOENT : CPBUS_EINVAL;
+  if (!b) return CPBUS_EINVAL;
+  if (id & CPBUS_EPHEMERAL_BIT) {
+    const uint32_t slot = id & 0xFFFFu, gen = (id >> 16) & 0x7FFFu;
+    if (slot >= b->eph.size() || !b->eph[slot].live || (b->eph[slot].gen & 0x7FFFu) != gen) return CPBUS_ENOENT;   // recycled
+    const std::string& s = b->eph[slot].s;
+    if (len) *len = s.size();
+    if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
+    return CPBUS_OK;
+  }
+  if (id >= b->sources.size()) return CPBUS_ENOENT;
   const std::string& s = b->sources[id];
   if (len) *len = s.size();
   if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
@@ -781,7 +876,10 @@ int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) {
     if (code >= CPBUS_N_CODES) return CPBUS_EINVAL;
     if ((rc = stage_one(b, code, ev[i].source_id, CPBUS_TARGET_ALL, 0))) return rc;
     const cpbus_event& e = b->h_batch[b->cur][b->n_staged - 1];
-    if (code != CPBUS_METRIC) b->st.published_by_code[code]++;   // events/bus.go:130-132
+    if (code != CPBUS_METRIC) {                                  // events/bus.go:130-132
+      b->st.published_by_code[code]++;
+      b->pub_pairs[((uint64_t)code << 32) | ev[i].source_id]++;
+    }
     dbg_enqueue(b, e);                                           // events/bus.go:139
     b->st.publishes++;
   }
@@ -842,14 +940,20 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
   b->now = watermark_ns;
   const cpbus_event* src = (const cpbus_event*)d_events;
   bool dep = false;
+  // Prefetch cache: a peer batch an earlier launch already pulled into d_prefetch[i].  An entry is good for ONE use, only
+  // while it is recent (the caller may re-stamp or reuse the peer buffer later), and the newest match wins.
+  for (int i = 0; i < cpbus::kPrefetch; i++)
+    if (b->pf_ptr[i] && b->launch_seq - b->pf_seq[i] > (unsigned long long)cpbus::kPrefetch) b->pf_ptr[i] = nullptr;
   if (staged && n) {
+    int hit = -1;
     for (int i = 0; i < cpbus::kPrefetch; i++)
-      if (b->pf_ptr[i] == d_events && b->pf_n[i] == n) {
-        src = b->d_prefetch[i];          // an earlier launch already pulled this batch over NVLink: plain local launch
-        staged = false;
-        dep = b->pf_seq[i] == b->launch_seq;   // written by the IMMEDIATELY preceding launch: its prologue must not run ahead
-        break;
-      }
+      if (b->pf_ptr[i] == d_events && b->pf_n[i] == n && (hit < 0 || b->pf_seq[i] > b->pf_seq[hit])) hit = i;
+    if (hit >= 0) {
+      src = b->d_prefetch[hit];          // plain local launch
+      staged = false;
+      dep = b->pf_seq[hit] == b->launch_seq;   // written by the IMMEDIATELY preceding launch: its prologue must not run ahead
+      for (int i = 0; i < cpbus::kPrefetch; i++) if (b->pf_ptr[i] == d_events) b->pf_ptr[i] = nullptr;   // consumed (and any older copy dropped)
+    }
   }
   const cpbus_event* pf_src = nullptr; cpbus_event* pf_dst = nullptr;
   int slot = -1;
@@ -857,8 +961,9 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
     slot = b->pf_next;
     if (b->d_prefetch[slot] == src) slot = (slot + 1) % cpbus::kPrefetch;   // never overwrite the buffer this launch reads
     pf_src = (const cpbus_event*)d_next; pf_dst = b->d_prefetch[slot];
+    for (int i = 0; i < cpbus::kPrefetch; i++) if (b->pf_ptr[i] == d_next) b->pf_ptr[i] = nullptr;   // superseded
   }
-  if ((rc = launch_fanout(b, src, (uint32_t)n, watermark_ns, staged, pf_src, pf_dst, (uint32_t)n_next, dep))) return rc;
+  if ((rc = launch_fanout(b, src, (uint32_t)n, watermark_ns, staged ? 1 : 0, pf_src, pf_dst, (uint32_t)n_next, dep, /*account=*/true))) return rc;
   if (slot >= 0) { b->pf_ptr[slot] = d_next; b->pf_n[slot] = n_next; b->pf_seq[slot] = b->launch_seq; b->pf_next = (slot + 1) % cpbus::kPrefetch; }
   b->st.publishes += n; b->seq += n;
   return CPBUS_OK;
@@ -908,11 +1013,213 @@ int cpbus_shared_close(cpbus_t* b, void* dptr) {
   if (!b || !dptr) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < cpbus::kPrefetch; i++) b->pf_ptr[i] = nullptr;   // prefetched copies of anything in that buffer are void
   for (size_t i = 0; i < b->shared_owned.size(); i++)
     if (b->shared_owned[i] == dptr) { cudaFree(dptr); b->shared_owned.erase(b->shared_owned.begin() + i); return CPBUS_OK; }
   for (size_t i = 0; i < b->shared_mapped.size(); i++)
     if (b->shared_mapped[i] == dptr) { cudaIpcCloseMemHandle(dptr); b->shared_mapped.erase(b->shared_mapped.begin() + i); return CPBUS_OK; }
   return CPBUS_ENOENT;
+}
+
+// ---- the publisher's event stream across the GPUs of one box (include/cpbus.h: cpbus_stream_*) ----
+struct cpbus_stream {
+  cpbus* bus = nullptr;
+  bool owner = false, attached = false;      // attached: same-process consumer sharing the owner's pointer (peer access, no IPC)
+  uint32_t n_slots = 0, n_consumers = 0, consumer = 0, B = 0;
+  unsigned char* base = nullptr;             // the ring: local memory on the publisher, NVLink peer mapping elsewhere
+  StreamHdr* hdr = nullptr;
+  unsigned long long* ack = nullptr;         // consumer c's word is ack[4 * c] (one sector each)
+  cpbus_event* payload = nullptr;
+  unsigned long long put_seq = 0, get_seq = 0;   // batches released / fanned out so far (ordinals are 1-based)
+  unsigned long long pub_seq = 0;            // publisher: publish ordinal stamped into the next record (CPBUS_PUT_STAMP)
+  unsigned long long min_ack = 0;            // publisher: cached min over the consumers' acks
+  // publisher staging: pinned payload + header buffers, copies on their own stream
+  static constexpr int kStage = 8;
+  cpbus_event* h_stage[kStage] = {};
+  StreamHdr* h_hdr = nullptr;                // kStage headers
+  unsigned long long* h_ack = nullptr;       // kStreamMaxConsumers x 4 words
+  cudaEvent_t staged_done[kStage] = {};
+  cudaStream_t put_stream = nullptr;
+};
+
+static int stream_bind(cpbus_stream* st) {
+  st->hdr = reinterpret_cast<StreamHdr*>(st->base + stream_hdr_off());
+  st->ack = reinterpret_cast<unsigned long long*>(st->base + stream_ack_off(st->n_slots));
+  st->payload = reinterpret_cast<cpbus_event*>(st->base + stream_payload_off(st->n_slots));
+  return CPBUS_OK;
+}
+
+int cpbus_stream_create(cpbus_t* b, uint32_t n_slots, uint32_t n_consumers, cpbus_stream_t** out, unsigned char handle[64]) {
+  if (!b || !out || !handle || n_slots < 4 || n_consumers == 0 || n_consumers > kStreamMaxConsumers) return CPBUS_EINVAL;
+  if (b->lossless) return CPBUS_EINVAL;   // admission would have to see every shard: throughput mode only
+  *out = nullptr;
+  int rc = dev_guard(b); if (rc) return rc;
+  cpbus_stream* st = new (std::nothrow) cpbus_stream();
+  if (!st) return CPBUS_ENOMEM;
+  st->bus = b; st->owner = true; st->n_slots = n_slots; st->n_consumers = n_consumers; st->consumer = 0; st->B = b->B;
+  st->pub_seq = b->seq;
+  const size_t bytes = stream_bytes(n_slots, b->B);
+  auto fail = [&](int code) { cpbus_stream_close(st); return code; };
+  b->streams.push_back(st);
+  if (cudaMalloc((void**)&st->base, bytes) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaMalloc(%zu) failed", bytes); return fail(CPBUS_ENOMEM); }
+  if (cudaMemset(st->base, 0, stream_payload_off(n_slots)) != cudaSuccess) return fail(CPBUS_ECUDA);
+  StreamMeta meta{}; meta.magic = kStreamMagic; meta.n_slots = n_slots; meta.batch_cap = b->B; meta.n_consumers = n_consumers;
+  if (cudaMemcpy(st->base, &meta, sizeof(meta), cudaMemcpyHostToDevice) != cudaSuccess) return fail(CPBUS_ECUDA);
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, st->base) != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaIpcGetMemHandle failed"); return fail(CPBUS_ECUDA); }
+  memcpy(handle, &h, 64);
+  stream_bind(st);
+  if (cudaStreamCreateWithFlags(&st->put_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
+  for (int i = 0; i < cpbus_stream::kStage; i++) {
+    if (cudaMallocHost((void**)&st->h_stage[i], (size_t)b->B * sizeof(cpbus_event)) != cudaSuccess) return fail(CPBUS_ENOMEM);
+    if (cudaEventCreateWithFlags(&st->staged_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CPBUS_ECUDA);
+  }
+  if (cudaMallocHost((void**)&st->h_hdr, sizeof(StreamHdr) * cpbus_stream::kStage) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  if (cudaMallocHost((void**)&st->h_ack, (size_t)kStreamMaxConsumers * 32) != cudaSuccess) return fail(CPBUS_ENOMEM);
+  *out = st;
+  return CPBUS_OK;
+}
+
+int cpbus_stream_open(cpbus_t* b, const unsigned char handle[64], uint32_t consumer_index, cpbus_stream_t** out) {
+  if (!b || !out || !handle || consumer_index == 0 || consumer_index >= kStreamMaxConsumers) return CPBUS_EINVAL;
+  if (b->lossless) return CPBUS_EINVAL;
+  *out = nullptr;
+  int rc = dev_guard(b); if (rc) return rc;      // the IMPORTING device must be current: the mapping is made for it
+  cpbus_stream* st = new (std::nothrow) cpbus_stream();
+  if (!st) return CPBUS_ENOMEM;
+  st->bus = b; st->owner = false; st->consumer = consumer_index;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle((void**)&st->base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); delete st; return CPBUS_ECUDA; }
+  StreamMeta meta{};
+  e = cudaMemcpy(&meta, st->base, sizeof(meta), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess || meta.magic != kStreamMagic || meta.batch_cap != b->B || consumer_index >= meta.n_consumers) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "stream meta mismatch (magic %x, batch_cap %u vs %u, consumers %u)", meta.magic, meta.batch_cap, b->B, meta.n_consumers);
+    cudaIpcCloseMemHandle(st->base); delete st;
+    return e != cudaSuccess ? CPBUS_ECUDA : CPBUS_EINVAL;
+  }
+  st->n_slots = meta.n_slots; st->n_consumers = meta.n_consumers; st->B = meta.batch_cap;
+  stream_bind(st);
+  b->streams.push_back(st);
+  *out = st;
+  return CPBUS_OK;
+}
+
+// Same-process consumer (one host process driving several GPUs, as a cgo shim would): no IPC handle — the owner's
+// pointer is used directly, with peer access enabled when the consumer's bus lives on another GPU.
+int cpbus_stream_attach(cpbus_t* b, cpbus_stream_t* owner, uint32_t consumer_index, cpbus_stream_t** out) {
+  if (!b || !owner || !owner->owner || !out || consumer_index == 0 || consumer_index >= owner->n_consumers) return CPBUS_EINVAL;
+  if (b->lossless || b->B != owner->B) return CPBUS_EINVAL;
+  *out = nullptr;
+  int rc = dev_guard(b); if (rc) return rc;
+  if (b->device != owner->bus->device) {
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, b->device, owner->bus->device));
+    if (!can) { snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d cannot access device %d", b->device, owner->bus->device); return CPBUS_ECUDA; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(owner->bus->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { CK(e); }
+    cudaGetLastError();   // clear "already enabled"
+  }
+  cpbus_stream* st = new (std::nothrow) cpbus_stream();
+  if (!st) return CPBUS_ENOMEM;
+  st->bus = b; st->attached = true; st->consumer = consumer_index;
+  st->n_slots = owner->n_slots; st->n_consumers = owner->n_consumers; st->B = owner->B; st->base = owner->base;
+  stream_bind(st);
+  b->streams.push_back(st);
+  *out = st;
+  return CPBUS_OK;
+}
+
+int cpbus_stream_close(cpbus_stream_t* st) {
+  if (!st) return CPBUS_EINVAL;
+  cpbus* b = st->bus;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  if (st->put_stream) { cudaStreamSynchronize(st->put_stream); cudaStreamDestroy(st->put_stream); }
+  for (int i = 0; i < cpbus_stream::kStage; i++) {
+    if (st->h_stage[i]) cudaFreeHost(st->h_stage[i]);
+    if (st->staged_done[i]) cudaEventDestroy(st->staged_done[i]);
+  }
+  if (st->h_hdr) cudaFreeHost(st->h_hdr);
+  if (st->h_ack) cudaFreeHost(st->h_ack);
+  if (st->base) { if (st->owner) cudaFree(st->base); else if (!st->attached) cudaIpcCloseMemHandle(st->base); }
+  b->streams.erase(std::remove(b->streams.begin(), b->streams.end(), st), b->streams.end());
+  delete st;
+  return CPBUS_OK;
+}
+
+int cpbus_stream_set_timeout(cpbus_stream_t* st, uint32_t microseconds) {
+  if (!st) return CPBUS_EINVAL;
+  st->bus->stream_spin_us = microseconds;
+  return CPBUS_OK;
+}
+
+int cpbus_stream_status(cpbus_stream_t* st) {
+  if (!st) return CPBUS_EINVAL;
+  return (*(volatile unsigned int*)st->bus->h_err) ? CPBUS_ETIMEDOUT : CPBUS_OK;
+}
+
+// Publisher: copy the batch into the next slot, then release it (header after payload, same stream).
+int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64_t now_ns, uint32_t flags) {
+  if (!st || !st->owner || (!ev && n) || n > st->B) return CPBUS_EINVAL;
+  cpbus* b = st->bus;
+  int rc = dev_guard(b); if (rc) return rc;
+  const unsigned long long q = st->put_seq + 1;
+  if (q > st->n_slots && st->min_ack + st->n_slots < q) {
+    // the slot still holds batch q - n_slots: every consumer must have pulled it (acks are device words: refresh the cache)
+    CK(cudaMemcpyAsync(st->h_ack, st->ack, (size_t)st->n_consumers * 32, cudaMemcpyDeviceToHost, st->put_stream));
+    CK(cudaStreamSynchronize(st->put_stream));
+    unsigned long long m = ~0ull;
+    for (uint32_t c = 0; c < st->n_consumers; c++) m = std::min(m, st->h_ack[4 * c]);
+    st->min_ack = m;
+    if (st->min_ack + st->n_slots < q) return CPBUS_EAGAIN;
+  }
+  const int s = (int)(q % cpbus_stream::kStage);
+  CK(cudaEventSynchronize(st->staged_done[s]));   // the pinned buffers of batch q - kStage have left the host
+  cpbus_event* dst = st->h_stage[s];
+  if (flags & CPBUS_PUT_RAW) { if (n) memcpy(dst, ev, n * sizeof(cpbus_event)); }
+  else {
+    for (size_t i = 0; i < n; i++) {
+      const uint32_t code = ev[i].code;
+      if (code >= CPBUS_N_CODES) return CPBUS_EINVAL;
+      dst[i].seq = st->pub_seq + i; dst[i].ts_ns = now_ns; dst[i].code = code; dst[i].source_id = ev[i].source_id;
+      dst[i].target = CPBUS_TARGET_ALL; dst[i].flags = 0;
+    }
+  }
+  const uint32_t slot = (uint32_t)(q % st->n_slots);
+  if (n) CK(cudaMemcpyAsync(st->payload + (size_t)slot * st->B, dst, n * sizeof(cpbus_event), cudaMemcpyHostToDevice, st->put_stream));
+  StreamHdr* hh = &st->h_hdr[s];
+  memset(hh, 0, sizeof(*hh));
+  hh->seq = q; hh->watermark = now_ns; hh->n = (uint32_t)n;
+  if (!(flags & CPBUS_PUT_RAW)) st->pub_seq += n;
+  CK(cudaMemcpyAsync(&st->hdr[slot], hh, sizeof(StreamHdr), cudaMemcpyHostToDevice, st->put_stream));   // the release: after the payload
+  CK(cudaEventRecord(st->staged_done[s], st->put_stream));
+  st->put_seq = q;
+  return CPBUS_OK;
+}
+
+// Every rank (the publisher's included): fan out the next batch of the stream to this GPU's shard.
+int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns) {
+  if (!st || n > st->B) return CPBUS_EINVAL;
+  cpbus* b = st->bus;
+  int rc = dev_guard(b); if (rc) return rc;
+  if (*(volatile unsigned int*)b->h_err) return CPBUS_ETIMEDOUT;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  if (now_ns < b->now) return CPBUS_EORDER;
+  if (now_ns - b->last_watermark > max_window(b)) return CPBUS_EORDER;
+  b->now = now_ns;
+  const unsigned long long q = st->get_seq + 1;
+  StreamArgs sa;
+  const uint32_t slot = (uint32_t)(q % st->n_slots), slot2 = (uint32_t)((q + 2) % st->n_slots);
+  sa.hdr = &st->hdr[slot]; sa.ack = &st->ack[4 * st->consumer]; sa.seq = q; sa.next_hdr = &st->hdr[slot2];
+  rc = launch_fanout(b, st->payload + (size_t)slot * st->B, (uint32_t)n, now_ns, /*staged=*/2,
+                     st->payload + (size_t)slot2 * st->B, b->d_pf_buf + (size_t)((q + 2) % kStreamPrefetch) * b->B, 0,
+                     /*batch_dep=*/false, /*account=*/true, &sa);
+  if (rc) return rc;
+  st->get_seq = q;
+  b->st.publishes += n; b->seq += n;
+  return CPBUS_OK;
 }
 
 static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head, uint64_t* lost = nullptr) {
@@ -1080,8 +1387,30 @@ int cpbus_step_result_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
 }
 
 // DebugEvents — events/bus.go:34-54
+// Broadcast events of device-published batches join the debug ring here, in publish order (the kernel's lead CTA kept
+// the last 10 of each such batch; launches older than kAcctDbgRing are no longer resolvable and are skipped).
+static int dbg_resolve(cpbus* b) {
+  if (b->dbg_pending.empty()) return CPBUS_OK;
+  bool any_marker = false;
+  for (const DbgItem& it : b->dbg_pending) any_marker |= it.marker;
+  if (any_marker) {
+    int rc = dev_guard(b); if (rc) return rc;
+    CK(cudaMemcpyAsync(b->h_acct->tail, b->d_acct->tail, sizeof(b->h_acct->tail), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
+  for (const DbgItem& it : b->dbg_pending) {
+    if (!it.marker) { dbg_ring_put(b, it.ev); continue; }
+    const DevDbgTail& t = b->h_acct->tail[it.launch % kAcctDbgRing];
+    if (t.launch_seq != it.launch) continue;
+    for (uint32_t j = 0; j < t.n_kept && j < (uint32_t)kAcctDbgKeep; j++) dbg_ring_put(b, t.ev[j]);
+  }
+  b->dbg_pending.clear();
+  return CPBUS_OK;
+}
+
 int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
+  { const int rc = dbg_resolve(b); if (rc) return rc; }
   size_t k = 0;
   for (;;) {
     if (b->dbg_head == -1) break;
@@ -1107,13 +1436,38 @@ int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(b->h_acct->by_code, b->d_acct->by_code, sizeof(b->h_acct->by_code), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   retire_oneshots(b, b->last_watermark);
   b->st.deliveries = b->st.ticks = 0;
   b->st.overwritten = b->h_stats->overwritten;
   for (int i = 0; i < kStatSlots; i++) { b->st.deliveries += b->h_stats->slot[i].deliveries; b->st.ticks += b->h_stats->slot[i].ticks; }
   b->st.n_subs = b->n_active; b->st.n_timers = b->n_timers; b->st.now_ns = b->now;
+  b->st.intern_entries = b->sources.size(); b->st.intern_bytes = b->intern_bytes;
+  b->st.ephemeral_live = b->eph_live; b->st.ephemeral_recycled = b->eph_recycled;
   *out = b->st;
+  for (int c = 0; c < CPBUS_N_CODES; c++) out->published_by_code[c] += b->h_acct->by_code[c];   // device-published batches (kernel-counted)
+  return CPBUS_OK;
+}
+
+// containerpilot_events{code, source} (events/bus.go:60-68,130-132): host publishes are counted in cpbus_publish, batches
+// that arrive in device memory by the fan-out kernel's lead CTA (DevPubAcct).
+int cpbus_publish_counts(cpbus_t* b, cpbus_pair_count* out, size_t cap, size_t* n) {
+  if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  std::unordered_map<uint64_t, uint64_t> merged = b->pub_pairs;
+  if (b->launch_seq) {
+    std::vector<unsigned long long> keys(kAcctPairSlots), cnts(kAcctPairSlots);
+    CK(cudaMemcpyAsync(keys.data(), b->d_acct->pair_key, sizeof(unsigned long long) * kAcctPairSlots, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(cnts.data(), b->d_acct->pair_cnt, sizeof(unsigned long long) * kAcctPairSlots, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (uint32_t i = 0; i < kAcctPairSlots; i++) if (keys[i]) merged[keys[i] - 1] += cnts[i];
+  }
+  std::vector<std::pair<uint64_t, uint64_t>> v(merged.begin(), merged.end());
+  std::sort(v.begin(), v.end());
+  for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = cpbus_pair_count{(uint32_t)(v[i].first >> 32), (uint32_t)v[i].first, v[i].second};
+  *n = v.size();
   return CPBUS_OK;
 }
 

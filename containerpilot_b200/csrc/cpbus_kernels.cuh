@@ -65,6 +65,26 @@ struct DevStats {
   unsigned long long admit_overflow, overwritten, pad[2];
 };
 
+// Accounting of batches that reach the bus already in device memory (cpbus_publish_device*, cpbus_stream_fanout).  What
+// cpbus_publish does on the host for host-staged events (events/bus.go:128-139) the fan-out kernel's lead CTA does here:
+// per-code publish counts (Metric excluded, bus.go:130), per-{code, source} counts (the label set of the
+// `containerpilot_events` counter, bus.go:131) and the last 10 broadcast events of the batch for the debug ring (bus.go:139).
+constexpr uint32_t kAcctPairSlots = 1u << 16;   // open addressing; key = (code << 32 | source_id) + 1, 0 = empty
+constexpr int kAcctDbgRing = 64, kAcctDbgKeep = 10;
+struct __align__(32) DevDbgTail {
+  unsigned long long launch_seq;                 // written last: the slot belongs to this launch
+  uint32_t n_broadcast, n_kept;
+  cpbus_event ev[kAcctDbgKeep];                  // the batch's last n_kept broadcast events, oldest first
+  uint32_t pad[4];
+};
+struct DevPubAcct {
+  unsigned long long by_code[32];
+  unsigned long long pair_overflow, pad[3];      // events whose {code, source} found no table slot
+  DevDbgTail tail[kAcctDbgRing];
+  unsigned long long pair_key[kAcctPairSlots];
+  unsigned long long pair_cnt[kAcctPairSlots];
+};
+
 // Per-subscriber control block: exactly one 32-byte sector, read once and written once
 // per subscriber per launch (the reference's hchan header: qcount/sendx/recvx, runtime/chan.go).
 struct __align__(32) SubCtl {
@@ -79,6 +99,20 @@ struct __align__(32) SubCtl {
 // that the per-CTA REDs do not serialise on one address; the host sums them).
 constexpr int kResultRing = 64, kResultSub = 8;
 struct __align__(32) DevResultSlot { unsigned long long deliveries, ticks, digest_sum, launch_seq; };
+
+// Publisher's event stream shared between the GPUs of one box (cpbus_stream_*): a ring of batch slots in the publisher
+// GPU's HBM.  A slot is complete when its header's seq equals the batch ordinal; the publisher writes the header AFTER
+// the payload (stream-ordered copies), consumers' CTA 0 acquires it over NVLink, pulls the payload and acknowledges.
+struct __align__(32) StreamHdr { unsigned long long seq, watermark; uint32_t n, pad[3]; };
+struct __align__(32) StreamMeta { uint32_t magic, n_slots, batch_cap, n_consumers, pad[4]; };
+constexpr uint32_t kStreamMagic = 0x53425043u;   // "CPBS"
+constexpr uint32_t kStreamMaxConsumers = 64;
+constexpr int kStreamPrefetch = 3;
+constexpr unsigned int kErrStreamTimeout = 1u, kErrStreamShape = 2u;
+__host__ __device__ inline size_t stream_hdr_off() { return sizeof(StreamMeta); }
+__host__ __device__ inline size_t stream_ack_off(uint32_t n_slots) { return stream_hdr_off() + (size_t)n_slots * sizeof(StreamHdr); }
+__host__ __device__ inline size_t stream_payload_off(uint32_t n_slots) { return stream_ack_off(n_slots) + (size_t)kStreamMaxConsumers * 32; }
+__host__ __device__ inline size_t stream_bytes(uint32_t n_slots, uint32_t batch_cap) { return stream_payload_off(n_slots) + (size_t)n_slots * batch_cap * 32; }
 
 struct FanoutParams {
   const cpbus_event* batch;   // n_ev records, sorted by ts (HBM)
@@ -104,8 +138,20 @@ struct FanoutParams {
   uint32_t n_ev, n_subs, ring_cap, K, sub_base;
   uint32_t use_digest, lossless, timers_on;
   uint32_t smem_cap;          // n_ev rounded up to 32 (shared-memory carve-up)
-  uint32_t hints;             // bit0: keep control blocks / timer slots in L2 (evict_last)
+  uint32_t hints;             // bit0: keep control blocks / timer slots in L2 (evict_last); bit1 (test hook): no CTA waits for
+                              // CTA 0's descriptor, every CTA builds its own (the bounded-spin fallback path)
   const uint2* pairs;         // PAIRS build: [n_subs][CPBUS_MAX_PAIRS] exact {code, source_id} cases (unused slot: code = kPairNone)
+  // ---- stream mode (staged == 2): the batch is slot `stream_seq % n_slots` of the publisher GPU's flagged ring ----
+  const StreamHdr* stream_hdr;       // this batch's header in the publisher's HBM (peer pointer on the other GPUs)
+  unsigned long long* stream_ack;    // this consumer's ack word in the publisher's HBM
+  unsigned long long stream_seq;     // 1-based ordinal of the batch this launch fans out
+  const StreamHdr* stream_next_hdr;  // header of batch stream_seq + 2 (prefetch_src = its payload), or nullptr
+  unsigned long long* pf_state;      // [kStreamPrefetch] local: pf_state[q % 3] == q  <=>  batch q sits in pf_buf slot q % 3
+  cpbus_event* pf_buf;               // kStreamPrefetch local buffers of pf_stride records
+  uint32_t pf_stride;
+  uint32_t spin_us;                  // bound of the cross-GPU flag wait (0 = default)
+  unsigned int* err_word;            // host-mapped: sticky error bits (kErr*)
+  DevPubAcct* acct;                  // non-null: this batch did not pass through cpbus_publish; the lead CTA accounts for it
 };
 
 // ---------------------------------------------------------------- helpers ---
@@ -195,6 +241,16 @@ __device__ __forceinline__ void st_half(void* dst, const uint4& a, bool hinted) 
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "l"(pol) : "memory");
   else st_v4(dst, a);
 }
+// One lane reads one staged 32-byte record as two 16-byte shared-memory loads.  At a 32-byte lane stride the eight lanes
+// of a quarter warp (one LDS.128 wavefront) touch only four distinct 16-byte bank groups: a 2-way conflict on every read
+// (round 1 ncu: l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld = 0.74 per record, 44 % of stall samples short_sb).
+// Lanes 4-7 of each quarter therefore fetch their two halves in the opposite order: each wavefront then covers all 32
+// banks, and two selects per register put the halves back in place.  No re-layout of the TMA-staged batch is needed.
+__device__ __forceinline__ void lds_record(const uint4* s4, uint32_t i, uint32_t sw, uint4& a, uint4& b) {
+  const uint4 x = s4[2 * i + sw], y = s4[2 * i + (sw ^ 1u)];
+  a.x = sw ? y.x : x.x; a.y = sw ? y.y : x.y; a.z = sw ? y.z : x.z; a.w = sw ? y.w : x.w;
+  b.x = sw ? x.x : y.x; b.y = sw ? x.y : y.y; b.z = sw ? x.z : y.z; b.w = sw ? x.w : y.w;
+}
 // TMA 1-D bulk copies (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -240,6 +296,10 @@ struct BatchSummary {
   uint32_t hist[32];       // broadcast events per code
   uint32_t acc_deliv, acc_ticks, acc_pad[2];   // per-CTA statistics (flushed once at exit)
   uint32_t acc_dig_lo, acc_dig_hi;                     // sum of fold32(new digest), as two 16-bit-limb sums (native 32-bit atomics)
+  uint32_t stream_local;   // stream mode: this batch was prefetched into local HBM by an earlier launch
+  uint32_t own_desc;       // this CTA builds the descriptor itself (CTA 0, or the bounded wait for CTA 0 ran out)
+  uint32_t abort_launch;   // the stream batch never arrived (publisher stalled): deliver nothing
+  uint32_t pf_ok;
   uint64_t red[kWarpsPerCta];
 };
 
@@ -275,17 +335,27 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // ---- stage the batch: one elected thread drives the TMA engine ----
   // Programmatic dependent launch: this kernel may begin while the previous fan-out is still draining its last wave.
   // Everything up to `griddepcontrol.wait` touches only data that the previous launch never writes (the batch, the
-  // power table, this launch's descriptor buffer); mailboxes, control blocks and timers come after it.
+  // power table, this launch's descriptor buffer, the publisher's stream); mailboxes, control blocks and timers come after it.
   if (p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (tid == 0) { mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0; }
+  const bool stream = p.staged == 2u;
+  const uint32_t pf_slot = stream ? (uint32_t)(p.stream_seq % kStreamPrefetch) : 0u;
+  if (tid == 0) {
+    mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0;
+    // stream mode: an earlier launch (two back, so it is complete and visible) may already hold this batch locally
+    s_sum->stream_local = (stream && __ldcg(p.pf_state + pf_slot) == p.stream_seq) ? 1u : 0u;
+    s_sum->abort_launch = 0; s_sum->own_desc = blockIdx.x == 0 ? 1u : 0u;
+  }
   __syncthreads();
+  const bool stream_local = stream && s_sum->stream_local;
+  // staged: the batch lives in another GPU's memory (or in the stream ring): CTA 0 pulls it once, stages it in local HBM
+  // and every other CTA takes CTA 0's local copy after the descriptor flag (second mbarrier phase)
+  const bool staged = p.staged && !stream_local;
+  const cpbus_event* batch_src = stream_local ? p.pf_buf + (size_t)pf_slot * p.pf_stride : p.batch;
   if (tid == 0) {   // two bulk copies on one mbarrier: the batch and the powers P^0..P^(cap+64)
     const uint32_t pow_bytes = ((cap + 65u) * 8u + 15u) & ~15u;
-    // staged mode (multi-GPU ingest fused into the fan-out): the batch is in the publisher GPU's memory; CTA 0 pulls it
-    // over NVLink once and every other CTA takes CTA 0's local copy after the descriptor flag (second mbarrier phase)
-    const bool direct = n && !p.staged;
+    const bool direct = n && !staged;
     mbar_expect_tx(&s_sum->mbar, (direct ? n * 32u : 0u) + pow_bytes);
-    if (direct) bulk_g2s(s_batch, p.batch, n * 32u, &s_sum->mbar);
+    if (direct) bulk_g2s(s_batch, batch_src, n * 32u, &s_sum->mbar);
     bulk_g2s(s_pow, p.pow_table, pow_bytes, &s_sum->mbar);
   }
 
@@ -293,30 +363,84 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // (the evict_last policy is materialised at each use — one instruction — rather than held in two registers)
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
-  // descriptor = [rhash | meta | Q] (24*cap + 16 bytes, same layout as shared memory) + {present, has_unicast, hist[32]}
+  // descriptor = [rhash | meta | Q] (24*cap + 16 bytes, same layout as shared memory) + {present, has_unicast, hist[32], abort}
   const uint32_t desc_words16 = (24u * cap + 16u) / 16u;
   uint4* s_desc = reinterpret_cast<uint4*>(s_rhash);
   uint4* g_desc = reinterpret_cast<uint4*>(p.desc);
   uint32_t* g_sum = reinterpret_cast<uint32_t*>(p.desc + (size_t)desc_words16 * 16u);
-  if (blockIdx.x == 0) {
-    if (tid < kResultSub * 4) reinterpret_cast<unsigned long long*>(p.result_next)[tid] = 0ull;   // next launch's result slot
+  if (blockIdx.x != 0) {
+    // Wait for CTA 0's descriptor — bounded.  CTA 0 is dispatched first and is resident in practice, but nothing
+    // guarantees it (MPS time slicing, preemption, a future scheduler): when the wait runs out this CTA builds the
+    // descriptor itself from the same batch (bit-identical result, only slower), so no CTA can spin forever.
+    if (tid == 0) {
+      unsigned long long seen = 0;
+      if (!(p.hints & 2u)) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long budget = stream ? 4000000000ull : 200000ull;   // ns; a stream batch may legitimately be late
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.desc_ready) : "memory");
+          if (seen >= p.launch_seq) break;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < budget);
+      }
+      if (seen < p.launch_seq) s_sum->own_desc = 1u;
+    }
+    __syncthreads();
+  }
+  const bool own_desc = s_sum->own_desc != 0;   // CTA-uniform
+  const bool lead = blockIdx.x == 0;            // the one CTA that publishes: descriptor, local batch copy, ack, result slot
+  if (own_desc) {
+    if (lead && tid < kResultSub * 4) reinterpret_cast<unsigned long long*>(p.result_next)[tid] = 0ull;   // next launch's result slot
     if (tid == 0) { s_sum->present = 0; s_sum->has_unicast = 0; }
     if (tid < 32) s_sum->hist[tid] = 0;
-    if (p.staged && n) {   // peer pull: plain 16-byte loads on the NVLink-mapped pointer, into shared memory and the local copy
+    if (stream && staged) {
+      // the publisher releases a slot by writing its header after the payload; acquire it across the link (bounded)
+      if (tid == 0) {
+        unsigned long long seen, t0, t1;
+        const unsigned long long budget = (p.spin_us ? (unsigned long long)p.spin_us : 2000000ull) * 1000ull;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&p.stream_hdr->seq) : "memory");
+          if (seen >= p.stream_seq) break;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > budget) break;
+          __nanosleep(64);
+        }
+        unsigned int err = 0;
+        if (seen != p.stream_seq) err = kErrStreamTimeout;   // never arrived (or the slot was already reused: the caller fell > n_slots behind)
+        else {
+          uint32_t hn;
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(hn) : "l"(&p.stream_hdr->n) : "memory");
+          if (hn != n) err = kErrStreamShape;
+        }
+        if (err) {
+          s_sum->abort_launch = 1u;
+          if (lead) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.err_word), "r"(err) : "memory");   // host-mapped, sticky
+        }
+      }
+      __syncthreads();
+    }
+    const bool aborted = s_sum->abort_launch != 0;
+    if (staged && n && !aborted) {   // peer pull: plain 16-byte loads on the NVLink-mapped pointer, into shared memory and the local copy
       const uint4* src = reinterpret_cast<const uint4*>(p.batch);
       uint4* loc = reinterpret_cast<uint4*>(p.batch_local);
       uint4* dst = reinterpret_cast<uint4*>(s_batch);
       for (uint32_t i = tid; i < 2 * n; i += kThreads) {
         uint4 v;
         asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
-        dst[i] = v; loc[i] = v;
+        dst[i] = v;
+        if (lead) loc[i] = v;
       }
     }
     mbar_wait(&s_sum->mbar, 0);
     __syncthreads();
+    if (lead && stream && tid == 0 && !aborted)   // the batch is out of the shared ring: the publisher may reuse the slot
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.stream_ack), "l"(p.stream_seq) : "memory");
+    const uint32_t nd = aborted ? 0u : n;
     {
       uint32_t present = 0, uni = 0;
-      for (uint32_t i = tid; i < n; i += kThreads) {
+      for (uint32_t i = tid; i < nd; i += kThreads) {
         const ulonglong4 w = *reinterpret_cast<const ulonglong4*>(&s_batch[i]);
         s_rhash[i] = record_hash_words(w.x, w.y, w.z, w.w);
         const uint32_t code = (uint32_t)w.z, target = (uint32_t)w.w;
@@ -333,10 +457,10 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     }
     __syncthreads();
     {   // Q: exclusive prefix sums of w_i = H(e_i) P^(n-1-i); Q[n] is the whole batch as one dense run
-      const uint32_t E = (n + kThreads - 1) / kThreads;
-      const uint32_t lo = min(n, (uint32_t)tid * E), hi = min(n, lo + E);
+      const uint32_t E = (nd + kThreads - 1) / kThreads;
+      const uint32_t lo = min(nd, (uint32_t)tid * E), hi = min(nd, lo + E);
       uint64_t sum = 0;
-      for (uint32_t i = lo; i < hi; i++) sum += s_rhash[i] * s_pow[n - 1 - i];
+      for (uint32_t i = lo; i < hi; i++) sum += s_rhash[i] * s_pow[nd - 1 - i];
       uint64_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -347,34 +471,63 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       __syncthreads();
       uint64_t run = incl - sum;
       for (int w = 0; w < warp; w++) run += s_sum->red[w];
-      for (uint32_t i = lo; i < hi; i++) { s_q[i] = run; run += s_rhash[i] * s_pow[n - 1 - i]; }
-      if (tid == 0) { uint64_t t = 0; for (int w = 0; w < kWarpsPerCta; w++) t += s_sum->red[w]; s_q[n] = t; }
+      for (uint32_t i = lo; i < hi; i++) { s_q[i] = run; run += s_rhash[i] * s_pow[nd - 1 - i]; }
+      if (tid == 0) { uint64_t t = 0; for (int w = 0; w < kWarpsPerCta; w++) t += s_sum->red[w]; s_q[nd] = t; }
       __syncthreads();
     }
-    for (uint32_t i = tid; i < desc_words16; i += kThreads) g_desc[i] = s_desc[i];
-    if (tid < 32) g_sum[2 + tid] = s_sum->hist[tid];
-    if (tid == 0) { g_sum[0] = s_sum->present; g_sum[1] = s_sum->has_unicast; }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
-  } else {
-    if (tid == 0) {
-      unsigned long long seen;
-      do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.desc_ready) : "memory"); } while (seen < p.launch_seq);
+    if (lead) {
+      for (uint32_t i = tid; i < desc_words16; i += kThreads) g_desc[i] = s_desc[i];
+      if (tid < 32) g_sum[2 + tid] = s_sum->hist[tid];
+      if (tid == 0) { g_sum[0] = s_sum->present; g_sum[1] = s_sum->has_unicast; g_sum[34] = s_sum->abort_launch; }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
+      if (p.acct && !aborted) {   // device-published batch: publish accounting (the other CTAs are already on their way)
+        if (tid < 32 && tid != CPBUS_METRIC && s_sum->hist[tid]) atomicAdd(&p.acct->by_code[tid], (unsigned long long)s_sum->hist[tid]);
+        for (uint32_t i = tid; i < nd; i += kThreads) {
+          if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
+          const uint32_t code = s_batch[i].code;
+          if (code == CPBUS_METRIC || code >= 32u) continue;
+          const unsigned long long key = (((unsigned long long)code << 32) | s_batch[i].source_id) + 1ull;
+          uint32_t slot = pair_key_hash(code, s_batch[i].source_id) & (kAcctPairSlots - 1u);
+          bool placed = false;
+          for (int probe = 0; probe < 256 && !placed; probe++, slot = (slot + 1u) & (kAcctPairSlots - 1u)) {
+            const unsigned long long old = atomicCAS(&p.acct->pair_key[slot], 0ull, key);
+            if (old == 0ull || old == key) { atomicAdd(&p.acct->pair_cnt[slot], 1ull); placed = true; }
+          }
+          if (!placed) atomicAdd(&p.acct->pair_overflow, 1ull);
+        }
+        if (tid == 0) {
+          DevDbgTail* t = &p.acct->tail[p.launch_seq % kAcctDbgRing];
+          uint32_t* idx = s_tick;                                      // warp 0's scratch is free until the main loop
+          uint32_t kept = 0, nb = 0;
+          for (uint32_t c = 0; c < 32; c++) nb += s_sum->hist[c];
+          for (uint32_t i = nd; i > 0 && kept < (uint32_t)kAcctDbgKeep; i--)
+            if (s_meta[i - 1].y == CPBUS_TARGET_ALL) idx[kept++] = i - 1;
+          for (uint32_t j = 0; j < kept; j++) t->ev[j] = s_batch[idx[kept - 1 - j]];
+          t->n_broadcast = nb; t->n_kept = kept;
+          __threadfence();
+          t->launch_seq = p.launch_seq;
+        }
+        __syncthreads();   // idx lives in the per-warp scratch the main loop is about to use
+      }
     }
-    if (p.staged && n && tid == 0) {
+  } else {
+    if (tid == 0) s_sum->abort_launch = __ldcg(g_sum + 34);
+    __syncthreads();
+    if (staged && n && tid == 0 && !s_sum->abort_launch) {
       mbar_wait(&s_sum->mbar, 0);                                    // phase 0 (power table) is over
       asm volatile("fence.proxy.async;" ::: "memory");               // CTA 0's generic-proxy stores -> our async-proxy read
       mbar_expect_tx(&s_sum->mbar, n * 32u);
       bulk_g2s(s_batch, p.batch_local, n * 32u, &s_sum->mbar);
     }
-    __syncthreads();
     for (uint32_t i = tid; i < desc_words16; i += kThreads) s_desc[i] = __ldcg(g_desc + i);
     if (tid < 32) s_sum->hist[tid] = __ldcg(g_sum + 2 + tid);
     if (tid == 0) { s_sum->present = __ldcg(g_sum); s_sum->has_unicast = __ldcg(g_sum + 1); }
-    mbar_wait(&s_sum->mbar, (p.staged && n) ? 1u : 0u);
+    mbar_wait(&s_sum->mbar, (staged && n && !s_sum->abort_launch) ? 1u : 0u);
     __syncthreads();
   }
+  const bool aborted = s_sum->abort_launch != 0;   // stream batch missing: this launch delivers nothing and fires no timer
   if (PAIRS) {   // the presence filter sits behind the per-warp scratch (the host adds kPairFilterBytes)
     uint32_t* s_present = s_tick + kWarpsPerCta * max(32u, cap / 2u);
     for (uint32_t i = tid; i < kPairFilterWords; i += kThreads) s_present[i] = 0u;
@@ -394,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // position space: plain build = subscriber index, strided over the grid; ORDERED build = index into p.order, one
   // contiguous block of p.spw positions per warp (lane l keeps the id at block position l: one coalesced load)
   uint32_t pos = ORDERED ? (blockIdx.x * kWarpsPerCta + warp) * p.spw : blockIdx.x * kWarpsPerCta + warp;
-  const uint32_t pos_end = ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs;
+  const uint32_t pos_end = aborted ? 0u : (ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs);
   const uint32_t pos_step = ORDERED ? 1u : wstride;
   uint32_t my_ids = 0;
   if (ORDERED && pos + lane < pos_end) my_ids = __ldg(p.order + pos + lane);
@@ -413,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const bool has_unicast = s_sum->has_unicast != 0;
   const uint32_t Rm = p.ring_cap - 1;
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
+  const uint32_t sw = ((uint32_t)lane >> 2) & 1u;                      // which half this lane fetches first (lds_record)
   const uint32_t scratch_words = max(32u, cap / 2u);                   // per warp: 32 tick positions or cap u16 event indices
   uint32_t* my_tick = s_tick + warp * scratch_words;
   bool bulk_pending = false;
@@ -514,7 +668,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         bulk_pending = true;
       } else if (STORE == CPBUS_STORE_V8) {
         for (uint32_t i = lane; i < n; i += 32) {
-          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          uint4 a, b;
+          lds_record(s4, i, sw, a, b);
           st_v8(ring + (((uint32_t)tail + i) & Rm), a, b);
         }
       } else {
@@ -540,7 +695,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         uint32_t out = i + t_idx;
         for (uint32_t t = t_idx; t < n_ticks && my_tick[t] < c0 + 32; t++) out += (my_tick[t] <= i) ? 1u : 0u;
         if (i < n) {
-          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          uint4 a, b;
+          lds_record(s4, i, sw, a, b);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
         }
       }
@@ -605,14 +761,17 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         uint32_t o = lane;
         for (; o + 32 < k; o += 64) {   // two outputs per lane per iteration: their index/record/hash loads are independent
           const uint32_t i0 = my_idx[o], i1 = my_idx[o + 32];
-          const uint4 a0 = s4[2 * i0], b0 = s4[2 * i0 + 1], a1 = s4[2 * i1], b1 = s4[2 * i1 + 1];
+          uint4 a0, b0, a1, b1;
+          lds_record(s4, i0, sw, a0, b0);
+          lds_record(s4, i1, sw, a1, b1);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
           st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
           if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
         }
         for (; o < k; o += 32) {
           const uint32_t i = my_idx[o];
-          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          uint4 a, b;
+          lds_record(s4, i, sw, a, b);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
           if (hashing) acc = acc * p32 + s_rhash[i];
         }
@@ -640,7 +799,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           const uint32_t w = __ballot_sync(0xffffffffu, match);
           if (match) {
             const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
-            const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+            uint4 a, b;
+            lds_record(s4, i, sw, a, b);
             st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
             if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
           }
@@ -705,7 +865,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           const uint32_t mrank = wp + __popc(w & ((1u << lane) - 1u));
           uint32_t out = mrank;
           for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= mrank) ? 1u : 0u;
-          const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+          uint4 a, b;
+          lds_record(s4, i, sw, a, b);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
           if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
         }
@@ -771,14 +932,38 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     if (blockIdx.x == 0) atomicAdd(&rs->launch_seq, p.launch_seq);
   }
   if (blockIdx.x == 0 && p.prefetch_src) {
-    // fused ingest: CTA 0 is done with its own mailboxes; pull the NEXT batch across NVLink now.  The link round trip
-    // hides under the stores of the CTAs still running, and the next launch starts from local memory.
-    const uint4* src = reinterpret_cast<const uint4*>(p.prefetch_src);
-    uint4* dst = reinterpret_cast<uint4*>(p.prefetch_dst);
-    for (uint32_t i = tid; i < 2 * p.prefetch_n; i += kThreads) {
-      uint4 v;
-      asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
-      dst[i] = v;
+    // fused ingest: CTA 0 is done with its own mailboxes; pull a LATER batch across NVLink now.  The link round trip
+    // hides under the stores of the CTAs still running, and that batch's launch starts from local memory.
+    uint32_t pn = p.prefetch_n;
+    bool go = true;
+    if (stream) {   // stream mode: only if the publisher has already released batch seq+2 (never wait for it here)
+      if (tid == 0) {
+        unsigned long long seen; uint32_t hn = 0;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&p.stream_next_hdr->seq) : "memory");
+        bool ok = !aborted && seen == p.stream_seq + 2;
+        if (ok) {
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(hn) : "l"(&p.stream_next_hdr->n) : "memory");
+          ok = hn <= p.pf_stride;
+        }
+        s_sum->pf_ok = ok ? hn + 1u : 0u;
+      }
+      __syncthreads();
+      go = s_sum->pf_ok != 0; pn = go ? s_sum->pf_ok - 1u : 0u;
+    }
+    if (go) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.prefetch_src);
+      uint4* dst = reinterpret_cast<uint4*>(p.prefetch_dst);
+      for (uint32_t i = tid; i < 2 * pn; i += kThreads) {
+        uint4 v;
+        asm volatile("ld.global.relaxed.sys.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+        dst[i] = v;
+      }
+      if (stream) {   // publish "batch seq+2 is local" to the launch after next (complete and visible before its prologue runs)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+          asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.pf_state + (p.stream_seq + 2) % kStreamPrefetch), "l"(p.stream_seq + 2) : "memory");
+      }
     }
   }
 }

@@ -69,7 +69,9 @@ enum {
   CPBUS_ENOENT = -6,   /* unknown subscriber / timer id                          */
   CPBUS_ECLOSED = -7,  /* subscriber already unsubscribed (Go: panic, bus.go:121)*/
   CPBUS_ENODEV = -8,   /* no CUDA device: there is NO CPU fallback               */
-  CPBUS_EORDER = -9    /* device batch not sorted by ts / clock moved backwards  */
+  CPBUS_EORDER = -9,   /* device batch not sorted by ts / clock moved backwards  */
+  CPBUS_ETIMEDOUT = -10 /* stream mode: a batch never arrived (publisher stalled or the consumer fell a whole ring
+                           behind); sticky: the bus reports it from every later stream call */
 };
 
 /* cpbus_config.flags */
@@ -121,6 +123,11 @@ typedef struct cpbus_stats_t {
   uint32_t n_subs;         /* currently subscribed                                */
   uint32_t n_timers;       /* currently armed                                     */
   uint64_t now_ns;         /* virtual clock                                       */
+  /* ABI v2 */
+  uint64_t intern_entries; /* permanent Source strings held by the intern table  */
+  uint64_t intern_bytes;   /* ... and their total length                          */
+  uint64_t ephemeral_live; /* payload strings currently held by the bounded ephemeral region (cpbus_intern_ephemeral) */
+  uint64_t ephemeral_recycled; /* ephemeral ids that have been recycled so far   */
 } cpbus_stats_t;
 
 typedef struct cpbus cpbus_t;
@@ -131,8 +138,18 @@ int cpbus_destroy(cpbus_t* bus);
 
 /* ---- Event.Source interning (events/events.go:12) ---- */
 int cpbus_intern(cpbus_t* bus, const char* s, size_t len, uint32_t* source_id);
-/* copies at most cap bytes; *len receives the full length */
+/* copies at most cap bytes; *len receives the full length.  CPBUS_ENOENT: unknown id, or an ephemeral id whose
+ * slot has been recycled since. */
 int cpbus_source(cpbus_t* bus, uint32_t source_id, char* out, size_t cap, size_t* len);
+/* Payload strings that are NOT names: every POST /v3/metric publishes Event{Metric, "key|value"}
+ * (control/endpoints.go:125-126) and each distinct value would otherwise live in the intern table for the bus's
+ * lifetime (the reference keeps Metric out of its per-source counter for the same cardinality reason, events/bus.go:130).
+ * Ephemeral ids come from a bounded region of CPBUS_EPHEMERAL_SLOTS strings that is recycled oldest-first: an id
+ * (bit 31 set) stays resolvable until CPBUS_EPHEMERAL_SLOTS newer distinct payloads have been interned — far beyond the
+ * lifetime of a record in a 1024-slot mailbox.  Equal strings that are both still live get the same id. */
+#define CPBUS_EPHEMERAL_SLOTS 65536u
+#define CPBUS_EPHEMERAL_BIT   0x80000000u
+int cpbus_intern_ephemeral(cpbus_t* bus, const char* s, size_t len, uint32_t* source_id);
 
 /* ---- membership: Subscribe/Unsubscribe (events/bus.go:105-122).  Ordered with
  *      publishes: any staged events are flushed first. ---- */
@@ -181,6 +198,8 @@ int cpbus_sync(cpbus_t* bus);
  * (seq/ts/target/flags set by the producer), sorted by ts_ns, n <= batch_cap,
  * 32-byte aligned.  watermark_ns >= last ts; becomes the bus clock. */
 int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
+/* (Batches published this way are accounted for by the kernel itself: cpbus_stats.published_by_code,
+ * cpbus_publish_counts and cpbus_debug_events see their broadcast events exactly as if they had gone through cpbus_publish.) */
 /* Same, but d_events may point into ANOTHER GPU's HBM (the publisher's event stream, peer-mapped over
  * NVLink, e.g. through CUDA IPC): one CTA of the fan-out kernel pulls the batch across the link, stages it
  * locally and hands it to the other CTAs together with the batch descriptor — the broadcast of SURVEY.md §8e
@@ -191,6 +210,41 @@ int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t 
  * launch runs (throughput mode only). */
 int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns,
                                 const void* d_next, size_t n_next);
+
+/* ---- the publisher's event stream across the GPUs of one box (one process per GPU) ----------------------------------
+ * The subscriber set partitions into contiguous shards, one bus per GPU (cpbus_config.sub_id_base); every shard must see
+ * the identical, totally ordered batch sequence.  A stream is a ring of n_slots batch slots in the
+ * PUBLISHER GPU's HBM, exported with CUDA IPC.  cpbus_stream_put copies a batch into the next slot and then releases it
+ * by writing the slot header {seq, watermark, n} (stream-ordered after the payload).  cpbus_stream_fanout, called by
+ * every rank including the publisher's, launches the ordinary fan-out kernel for the next batch of the stream: its lead
+ * CTA acquires the header across NVLink (ld.acquire.sys, bounded wait), pulls the 32-byte records over the peer mapping,
+ * stages them locally for the other CTAs and acknowledges the slot (st.release.sys into the publisher's memory) — the
+ * broadcast is fused into the fan-out launch; there is no collective, no copy-engine op and no cross-stream wait on the
+ * consumers' data path.  When the publisher runs >= 2 batches ahead, the lead CTA of batch q also pulls batch q+2 while
+ * its own stores are in flight, so later launches start from local memory and keep their prologue overlapped with the
+ * previous launch (programmatic dependent launch).  Throughput (overwrite-oldest) mode only.
+ *   publisher rank : cpbus_stream_create(bus, n_slots, n_consumers, &st, handle); send `handle` to the other ranks
+ *   other ranks    : cpbus_stream_open(bus, handle, consumer_index (1..n_consumers-1), &st)
+ *   every step     : [publisher] cpbus_stream_put(st, events, n, now_ns, flags)   (may run ahead by < n_slots batches)
+ *                    [all ranks] cpbus_stream_fanout(st, n, now_ns)
+ * The consumers must be told n and now_ns of every batch by the caller (SPMD drivers know them; the header carries both
+ * and the kernel cross-checks n).  CPBUS_EAGAIN from _put: the slot's previous batch is not yet acknowledged by every
+ * consumer — call again after the consumers have advanced.  CPBUS_ETIMEDOUT from _fanout/_status: an earlier stream
+ * launch gave up waiting for its batch (bounded in-kernel wait, cpbus_stream_set_timeout) and delivered nothing. */
+typedef struct cpbus_stream cpbus_stream_t;
+#define CPBUS_PUT_STAMP 0x0u /* records are stamped like cpbus_publish: seq = running publish ordinal, ts = now_ns,
+                                target = ALL, flags = 0; only code/source_id are read from the caller's records */
+#define CPBUS_PUT_RAW   0x1u /* records are complete (as for cpbus_publish_device): copied verbatim */
+int cpbus_stream_create(cpbus_t* bus, uint32_t n_slots, uint32_t n_consumers, cpbus_stream_t** out, unsigned char handle[64]);
+int cpbus_stream_open(cpbus_t* bus, const unsigned char handle[64], uint32_t consumer_index, cpbus_stream_t** out);
+/* same-process consumer (one host process driving several GPUs, as the cgo shim does): no IPC handle, the owner's ring is
+ * used through peer access (enabled here if the two buses live on different GPUs) */
+int cpbus_stream_attach(cpbus_t* bus, cpbus_stream_t* owner, uint32_t consumer_index, cpbus_stream_t** out);
+int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* events, size_t n, uint64_t now_ns, uint32_t flags);
+int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns);
+int cpbus_stream_status(cpbus_stream_t* st);                       /* CPBUS_OK or the sticky error */
+int cpbus_stream_set_timeout(cpbus_stream_t* st, uint32_t microseconds);   /* in-kernel wait bound; default 2 s */
+int cpbus_stream_close(cpbus_stream_t* st);                        /* importers close before the owner */
 
 /* Buffers shared between the GPUs (processes) of one box, for the publisher's event stream: _alloc makes a
  * device buffer on this bus's GPU and returns a 64-byte CUDA IPC handle; _open, called on ANOTHER bus (another
@@ -234,6 +288,11 @@ int cpbus_step_result_end(cpbus_t* bus, uint32_t ticket, uint64_t out[4]);
  * events, oldest first, stopping at a NonEvent.  Host-side, no 100 ms sleep. */
 int cpbus_debug_events(cpbus_t* bus, cpbus_event* out, size_t cap, size_t* n);
 int cpbus_stats(cpbus_t* bus, cpbus_stats_t* out);
+/* Publish counts by {code, source}: the label set of the reference's `containerpilot_events` counter
+ * (events/bus.go:60-68,130-132; code Metric is excluded there and here).  Covers both host publishes and batches that
+ * reached the bus in device memory (counted by the kernel).  Writes at most cap entries, *n = entries available. */
+typedef struct cpbus_pair_count { uint32_t code, source_id; uint64_t count; } cpbus_pair_count;
+int cpbus_publish_counts(cpbus_t* bus, cpbus_pair_count* out, size_t cap, size_t* n);
 /* HBM layout, for zero-copy inspection by tests/bench: `ring` = n_max_subs mailboxes of
  * ring_cap records each (mailbox s starts at ring + s*ring_cap*32 bytes; slot of the j-th
  * delivered record = j mod ring_cap); `ctl` = n_max_subs control blocks of 32 bytes:

@@ -318,6 +318,32 @@ int orc_publish_many(orc_bus* b, const uint32_t* codes, const uint32_t* sources,
   return ORC_OK;
 }
 
+/* Complete records, as cpbus_publish_device / cpbus_stream_put(CPBUS_PUT_RAW) take them (bench traces, multi-GPU
+ * streams): the clock first reaches each record's ts (timers due by then fire before it, timer.go:59-67); a broadcast
+ * record is then delivered exactly like Publish (bus.go:125-140) and a unicast one like Receive (subscriber.go:30-32),
+ * but with the record's OWN seq/ts.  A unicast target outside this shard is some other shard's business.  Finally the
+ * clock reaches `watermark`. */
+int orc_publish_records(orc_bus* b, const orc_event* recs, size_t n, uint64_t watermark_ns) {
+  for (size_t r = 0; r < n; r++) {
+    const orc_event* e = &recs[r];
+    if (e->ts_ns > b->now) { int rc = orc_advance(b, e->ts_ns); if (rc) return rc; }
+    if (e->target == ORC_TARGET_ALL) {
+      if (e->code != ORC_METRIC && e->code < ORC_N_CODES) b->by_code[e->code]++;
+      for (uint32_t i = 0; i < b->n_next; i++) {
+        orc_sub* s = &b->subs[i];
+        if (s->active && wants(s, e->code, e->source_id)) receive(b, s, e);
+      }
+      enqueue(b, e);
+    } else {
+      orc_sub* s = sub_at(b, e->target);
+      if (s && s->active) receive(b, s, e);
+    }
+    b->seq = e->seq + 1;
+  }
+  if (watermark_ns > b->now) return orc_advance(b, watermark_ns);
+  return ORC_OK;
+}
+
 /* ------------------------------------------------------------ observers --- */
 uint64_t orc_count(orc_bus* b, uint32_t gid) { orc_sub* s = sub_at(b, gid); return s ? s->count : 0; }
 uint64_t orc_digest(orc_bus* b, uint32_t gid) { orc_sub* s = sub_at(b, gid); return s ? s->digest : 0; }

@@ -77,6 +77,8 @@ int orc_wait(orc_bus*);          /* 0/1 = reload flag; -1 = would block (done co
 int orc_publish(orc_bus*, uint32_t code, uint32_t source_id);
 int orc_publish_many(orc_bus*, const uint32_t* codes, const uint32_t* sources, size_t n,
                      uint64_t dt_ns /* advance by dt before each publish; 0 = none */);
+/* complete records (cpbus_publish_device / CPBUS_PUT_RAW semantics): clock -> each ts, deliver verbatim, clock -> watermark */
+int orc_publish_records(orc_bus*, const orc_event* recs, size_t n, uint64_t watermark_ns);
 int orc_receive(orc_bus*, uint32_t sub_id, uint32_t code, uint32_t source_id);
 int orc_advance(orc_bus*, uint64_t now_ns);
 int orc_timer_add(orc_bus*, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id);
@@ -107,6 +109,11 @@ double gobus_bench(uint32_t n_subs, uint32_t n_events, uint32_t mailbox_cap,
 /* step-structured variant (threads/channels created once; `warmup` untimed steps, then `steps` timed ones) */
 double gobus_bench_steps(uint32_t n_subs, uint32_t events_per_step, uint32_t steps, uint32_t warmup, uint32_t mailbox_cap,
                          uint32_t n_threads, double* seconds_out);
+
+/* round 2: pinned threads, NUMA-local mailboxes, per-step times (warmup + steps doubles), optional send-only
+ * (overwrite-oldest, no consumer: what the GPU arm's throughput mode does) */
+double gobus_bench_steps2(uint32_t n_subs, uint32_t events_per_step, uint32_t steps, uint32_t warmup, uint32_t mailbox_cap,
+                          uint32_t n_threads, int send_only, double* step_seconds_out);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ def lib():
             "orc_register": (C.c_int, [vp]), "orc_unregister": (C.c_int, [vp]), "orc_set_reload": (None, [vp]),
             "orc_wait": (C.c_int, [vp]), "orc_publish": (C.c_int, [vp, u32, u32]),
             "orc_publish_many": (C.c_int, [vp, vp, vp, C.c_size_t, u64]),
+            "orc_publish_records": (C.c_int, [vp, vp, C.c_size_t, u64]),
             "orc_receive": (C.c_int, [vp, u32, u32, u32]), "orc_advance": (C.c_int, [vp, u64]),
             "orc_timer_add": (C.c_int, [vp, u32, u64, u32, C.c_int, C.POINTER(u32)]),
             "orc_timer_cancel": (C.c_int, [vp, u32]), "orc_debug_events": (C.c_size_t, [vp, vp, C.c_size_t]),
@@ -38,6 +39,7 @@ def lib():
             "orc_digest_multiplier": (u64, []),
             "gobus_bench": (C.c_double, [u32, u32, u32, u32, C.POINTER(u64)]),
             "gobus_bench_steps": (C.c_double, [u32, u32, u32, u32, u32, u32, C.POINTER(C.c_double)]),
+            "gobus_bench_steps2": (C.c_double, [u32, u32, u32, u32, u32, u32, C.c_int, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -93,6 +95,11 @@ class Oracle:
         c = np.ascontiguousarray(codes, dtype=np.uint32)
         s = np.ascontiguousarray(sources, dtype=np.uint32)
         return self.l.orc_publish_many(self.h, c.ctypes.data, s.ctypes.data, c.size, dt_ns)
+
+    def publish_records(self, records, watermark_ns=0):
+        """complete 32-byte records (cpbus_publish_device / CPBUS_PUT_RAW semantics)"""
+        r = np.ascontiguousarray(records, dtype=EVENT_DTYPE)
+        return self.l.orc_publish_records(self.h, r.ctypes.data, r.size, watermark_ns)
 
     def receive(self, sub, code, source_id=0):
         return self.l.orc_receive(self.h, sub, code, source_id)
@@ -154,3 +161,10 @@ def gobus_bench_steps(n_subs, events_per_step, steps, warmup, mailbox_cap=1000, 
     sec = C.c_double()
     v = lib().gobus_bench_steps(n_subs, events_per_step, steps, warmup, mailbox_cap, n_threads, C.byref(sec))
     return v, sec.value
+
+
+def gobus_bench_steps2(n_subs, events_per_step, steps, warmup, mailbox_cap=1000, n_threads=1, send_only=False):
+    """(deliveries/s over the timed steps, per-step seconds of the timed steps) — pinned threads, NUMA-local mailboxes."""
+    sec = np.zeros(steps + warmup, dtype=np.float64)
+    v = lib().gobus_bench_steps2(n_subs, events_per_step, steps, warmup, mailbox_cap, n_threads, int(send_only), sec.ctypes.data)
+    return v, sec[warmup:].copy()

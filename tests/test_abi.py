@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libcpbus.so does not export {n}"
     assert set(names) == set(nat.SYMBOLS), set(names) ^ set(nat.SYMBOLS)
-    assert nat.load().cpbus_abi_version() == 1
+    assert nat.load().cpbus_abi_version() == 2
 
 
 def test_record_layout_is_32_bytes():
