@@ -71,6 +71,7 @@ SYMBOLS = {
     "cpbus_subscribe_pairs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _P(C.c_uint32)]),
     "cpbus_subscribe_pairs_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, _P(C.c_uint32)]),
     "cpbus_unsubscribe": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "cpbus_set_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cpbus_timer_add": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, _P(C.c_uint32)]),
     "cpbus_timer_add_many": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]),
     "cpbus_timer_cancel": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -106,6 +106,9 @@ class Bus:
                   "cpbus_subscribe_pairs_many")
         return out.value
 
+    def set_mask(self, sub_id: int, mask: int):
+        nat.check(self._lib.cpbus_set_mask(self._h, sub_id, mask), "cpbus_set_mask")
+
     def unsubscribe(self, sub_id: int):
         nat.check(self._lib.cpbus_unsubscribe(self._h, sub_id), "cpbus_unsubscribe")
 

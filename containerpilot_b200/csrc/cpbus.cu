@@ -38,7 +38,9 @@ thread_local char g_cuda_err[256] = "";
 // debug ring entry awaiting enqueue: a concrete event, or "the broadcast events of device launch `launch`"
 struct DbgItem { bool marker; unsigned long long launch; cpbus_event ev; };
 
-struct HostTimer { bool active = false, oneshot = false; uint64_t period = 0, next_due = 0; uint32_t source_id = 0; };
+struct HostTimer { bool active = false, oneshot = false; uint8_t gen = 0; uint64_t period = 0, next_due = 0; uint32_t source_id = 0; };
+// timer id = slot index (subscriber * K + k) | generation << 26: a late cancel from an old context cannot disarm a re-armed slot
+constexpr uint32_t kTimerSlotBits = 26, kTimerSlotMask = (1u << kTimerSlotBits) - 1u;
 
 }  // namespace
 
@@ -476,6 +478,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   const uint32_t K = cfg->timers_per_sub;
   if (!cfg->n_max_subs || !is_pow2(R) || R < 64 || B == 0 || B > R / 2 || (B % 32) != 0 || B > 1024) return CPBUS_EINVAL;   // 1024: the kernel keeps one match word per 32-event chunk in a lane
   if (!(K == 0 || K == 1 || K == 2 || K == 4 || K == 8)) return CPBUS_EINVAL;
+  if ((uint64_t)cfg->n_max_subs * std::max(K, 1u) > kTimerSlotMask) return CPBUS_EINVAL;   // timer ids keep 6 generation bits
   if (cfg->store_path > CPBUS_STORE_BULK) return CPBUS_EINVAL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -783,6 +786,23 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   return CPBUS_OK;
 }
 
+// Change a subscriber's code mask in place (ordered with publishes like Subscribe): the subscriber keeps its mailbox,
+// its timers and its exact cases.  Used when a mailbox that so far only received timer ticks / direct sends (mask 0:
+// NewEventTimer on a channel that was not subscribed, watches/watches.go:37,71) is subscribed to the bus after all.
+int cpbus_set_mask(cpbus_t* b, uint32_t sub_id, uint32_t mask) {
+  if (!b) return CPBUS_EINVAL;
+  const uint32_t l = sub_id - b->cfg.sub_id_base;
+  if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
+  if (!b->h_active[l]) return CPBUS_ECLOSED;
+  int rc = dev_guard(b); if (rc) return rc;
+  if ((rc = flush_staged(b, b->now))) return rc;
+  mask &= CPBUS_MASK_ALL;
+  if (b->h_mask[l] != CPBUS_MASK_ALL) b->n_filtered--;
+  if (mask != CPBUS_MASK_ALL) b->n_filtered++;
+  b->h_mask[l] = mask; b->order_dirty = true;
+  return push_mask_words(b, l, 1);
+}
+
 static int push_mask_words(cpbus* b, uint32_t first, uint32_t n) {
   std::vector<uint32_t> words(n);
   for (uint32_t i = 0; i < n; i++) words[i] = mask_word(b, first + i);
@@ -811,7 +831,8 @@ int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t so
     b->n_timers++;
     if (!oneshot) b->min_period = std::min(b->min_period, period_ns);
     else b->oneshot_idx.push_back((size_t)l * b->K + k);
-    if (timer_id) *timer_id = l * b->K + k;
+    t.gen = (uint8_t)((t.gen + 1) & 0x3F);
+    if (timer_id) *timer_id = (l * b->K + k) | ((uint32_t)t.gen << kTimerSlotBits);
     return push_mask_words(b, l, 1);
   }
   return CPBUS_ENOSPC;
@@ -854,13 +875,14 @@ int cpbus_timer_add_many(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t pe
 int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
   if (!b) return CPBUS_EINVAL;
   if (!b->K || b->h_timers.empty()) return CPBUS_ENOENT;
-  const uint32_t l = timer_id / b->K, k = timer_id % b->K;
+  const uint32_t slot_index = timer_id & kTimerSlotMask, gen = timer_id >> kTimerSlotBits;
+  const uint32_t l = slot_index / b->K, k = slot_index % b->K;
   if (l >= b->n_next) return CPBUS_ENOENT;
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = flush_staged(b, b->now))) return rc;   // firings due before the cancel still happen
   retire_oneshots(b, b->last_watermark);
   HostTimer& t = b->h_timers[(size_t)l * b->K + k];
-  if (!t.active) return CPBUS_ENOENT;
+  if (!t.active || t.gen != gen) return CPBUS_ENOENT;   // already fired / cancelled, or the slot has been re-armed since
   t.active = false; b->n_timers--;
   CK(cudaMemsetAsync(b->d_timers + (size_t)l * b->K + k, 0xFF, sizeof(DevTimer), b->stream));
   CK(cudaStreamSynchronize(b->stream));

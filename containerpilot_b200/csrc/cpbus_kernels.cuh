@@ -69,7 +69,7 @@ struct DevStats {
 // cpbus_publish does on the host for host-staged events (events/bus.go:128-139) the fan-out kernel's lead CTA does here:
 // per-code publish counts (Metric excluded, bus.go:130), per-{code, source} counts (the label set of the
 // `containerpilot_events` counter, bus.go:131) and the last 10 broadcast events of the batch for the debug ring (bus.go:139).
-constexpr uint32_t kAcctPairSlots = 1u << 16;   // open addressing; key = (code << 32 | source_id) + 1, 0 = empty
+constexpr uint32_t kAcctPairSlots = 1u << 19;   // open addressing (8 MiB of HBM); key = (code << 32 | source_id) + 1, 0 = empty
 constexpr int kAcctDbgRing = 64, kAcctDbgKeep = 10;
 struct __align__(32) DevDbgTail {
   unsigned long long launch_seq;                 // written last: the slot belongs to this launch
@@ -287,13 +287,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 //   [0, 32cap)            staged batch (TMA destination)
 //   [32cap, 40cap)        record hashes H(e_i)
 //   [40cap, 48cap)        {codebit, target} per event
-//   [48cap, 56cap+8)      Q[i] = sum_{j<i} H(e_j) P^(n-1-j): prefix sums for O(#ticks) digests of dense runs
-//   then                  powers P^0 .. P^(cap+64), batch summary, per-warp tick scratch
+//   [48cap, 56cap+16)     Q[i] = sum_{j<i} H(e_j) P^(n-1-j): prefix sums for O(#ticks) digests of dense runs
+//   [.., +160)            descriptor summary {present, has_unicast, hist[32]} (lands with the descriptor's bulk copy)
+//   then                  powers P^0 .. P^(cap+64), BatchSummary (mbarriers, per-CTA accumulators), per-warp tick scratch
 struct BatchSummary {
   uint64_t mbar;
-  uint32_t present;        // OR of codebits of the broadcast events
-  uint32_t has_unicast;    // any record with a specific target
-  uint32_t hist[32];       // broadcast events per code
+  uint64_t mbar_desc;      // the descriptor's bulk copy (CTAs other than the one that built it)
   uint32_t acc_deliv, acc_ticks, acc_pad[2];   // per-CTA statistics (flushed once at exit)
   uint32_t acc_dig_lo, acc_dig_hi;                     // sum of fold32(new digest), as two 16-bit-limb sums (native 32-bit atomics)
   uint32_t stream_local;   // stream mode: this batch was prefetched into local HBM by an earlier launch
@@ -303,11 +302,11 @@ struct BatchSummary {
   uint64_t red[kWarpsPerCta];
 };
 
-__host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 34 * 4 + 8; }
+__host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 160; }
 
 __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
   const size_t scratch = (cap / 2u > 32u ? cap / 2u : 32u) * sizeof(uint32_t);
-  return (size_t)cap * 56 + 16 + (size_t)(cap + 66) * 8 + sizeof(BatchSummary) + kWarpsPerCta * scratch + 128;
+  return (size_t)cap * 56 + 16 + 160 + (size_t)(cap + 66) * 8 + sizeof(BatchSummary) + kWarpsPerCta * scratch + 128;
 }
 
 // TIMERS=false compiles every timer/tick path out (the host knows when no timer is armed): fewer registers,
@@ -325,7 +324,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   uint64_t* s_rhash = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 32);
   uint2* s_meta = reinterpret_cast<uint2*>(smem + (size_t)cap * 40);
   uint64_t* s_q = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 48);
-  uint64_t* s_pow = s_q + cap + 2;                                   // 16-byte aligned (TMA destination)
+  uint32_t* s_dsum = reinterpret_cast<uint32_t*>(s_q + cap + 2);        // descriptor summary: present, has_unicast, hist[32], pad (160 B)
+  uint64_t* s_pow = s_q + cap + 2 + 20;                              // 16-byte aligned (TMA destination)
   BatchSummary* s_sum = reinterpret_cast<BatchSummary*>(s_pow + cap + 66);
   uint32_t* s_tick = reinterpret_cast<uint32_t*>(s_sum + 1);
 
@@ -339,11 +339,24 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   if (p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
   const bool stream = p.staged == 2u;
   const uint32_t pf_slot = stream ? (uint32_t)(p.stream_seq % kStreamPrefetch) : 0u;
+  // position space: plain build = subscriber index, strided over the grid; ORDERED build = index into p.order, one
+  // contiguous block of p.spw positions per warp (lane l keeps the id at block position l: one coalesced load)
+  uint32_t pos = ORDERED ? (blockIdx.x * kWarpsPerCta + warp) * p.spw : blockIdx.x * kWarpsPerCta + warp;
+  uint32_t my_ids = 0;
+  if (ORDERED && pos + lane < min(pos + p.spw, p.n_order)) my_ids = __ldg(p.order + pos + lane);   // static data: safe before the wait
+  if (!ORDERED && pos < p.n_subs && lane == 0) {
+    // the first control block (and timer slot) of this warp: pull it towards L2 now, so that the load after the prologue
+    // does not pay a DRAM round trip behind the write stream.  L2 is the point of coherence: a prefetch can never make
+    // the later load see stale data, so this is safe before griddepcontrol.wait.
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ctl + pos));
+    if (TIMERS && p.timers_on && p.K) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.timers + (size_t)pos * p.K));
+  }
   if (tid == 0) {
-    mbar_init(&s_sum->mbar, 1); s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0;
+    mbar_init(&s_sum->mbar, 1); mbar_init(&s_sum->mbar_desc, 1);
+    s_sum->acc_deliv = 0; s_sum->acc_ticks = 0; s_sum->acc_dig_lo = 0; s_sum->acc_dig_hi = 0;
     // stream mode: an earlier launch (two back, so it is complete and visible) may already hold this batch locally
     s_sum->stream_local = (stream && __ldcg(p.pf_state + pf_slot) == p.stream_seq) ? 1u : 0u;
-    s_sum->abort_launch = 0; s_sum->own_desc = blockIdx.x == 0 ? 1u : 0u;
+    s_sum->own_desc = blockIdx.x == 0 ? 1u : 0u; s_sum->abort_launch = 0;
   }
   __syncthreads();
   const bool stream_local = stream && s_sum->stream_local;
@@ -363,11 +376,13 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // (the evict_last policy is materialised at each use — one instruction — rather than held in two registers)
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
-  // descriptor = [rhash | meta | Q] (24*cap + 16 bytes, same layout as shared memory) + {present, has_unicast, hist[32], abort}
-  const uint32_t desc_words16 = (24u * cap + 16u) / 16u;
+  // descriptor = [rhash | meta | Q | summary {present, has_unicast, hist[32]}]: 24*cap + 16 + 160 bytes, the same layout in
+  // shared memory and in HBM, so the copy is ONE bulk (TMA) transfer per CTA.  The flag word carries the launch ordinal and,
+  // in bit 63, "aborted" (stream batch missing), so a consumer needs no second load to learn it.
+  const uint32_t desc_bytes = 24u * cap + 16u + 160u;
   uint4* s_desc = reinterpret_cast<uint4*>(s_rhash);
   uint4* g_desc = reinterpret_cast<uint4*>(p.desc);
-  uint32_t* g_sum = reinterpret_cast<uint32_t*>(p.desc + (size_t)desc_words16 * 16u);
+  constexpr unsigned long long kAbortBit = 1ull << 63;
   if (blockIdx.x != 0) {
     // Wait for CTA 0's descriptor — bounded.  CTA 0 is dispatched first and is resident in practice, but nothing
     // guarantees it (MPS time slicing, preemption, a future scheduler): when the wait runs out this CTA builds the
@@ -380,11 +395,23 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         const unsigned long long budget = stream ? 4000000000ull : 200000ull;   // ns; a stream batch may legitimately be late
         do {
           asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(p.desc_ready) : "memory");
-          if (seen >= p.launch_seq) break;
+          if ((seen & ~kAbortBit) >= p.launch_seq) break;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         } while (t1 - t0 < budget);
       }
-      if (seen < p.launch_seq) s_sum->own_desc = 1u;
+      if ((seen & ~kAbortBit) < p.launch_seq) s_sum->own_desc = 1u;
+      else {
+        const bool ab = (seen & kAbortBit) != 0;
+        s_sum->abort_launch = ab ? 1u : 0u;
+        asm volatile("fence.proxy.async;" ::: "memory");             // CTA 0's generic-proxy stores -> our async-proxy reads
+        mbar_expect_tx(&s_sum->mbar_desc, desc_bytes);
+        bulk_g2s(s_desc, g_desc, desc_bytes, &s_sum->mbar_desc);
+        if (staged && n && !ab) {
+          mbar_wait(&s_sum->mbar, 0);                                // phase 0 (power table) is over
+          mbar_expect_tx(&s_sum->mbar, n * 32u);
+          bulk_g2s(s_batch, p.batch_local, n * 32u, &s_sum->mbar);
+        }
+      }
     }
     __syncthreads();
   }
@@ -392,8 +419,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const bool lead = blockIdx.x == 0;            // the one CTA that publishes: descriptor, local batch copy, ack, result slot
   if (own_desc) {
     if (lead && tid < kResultSub * 4) reinterpret_cast<unsigned long long*>(p.result_next)[tid] = 0ull;   // next launch's result slot
-    if (tid == 0) { s_sum->present = 0; s_sum->has_unicast = 0; }
-    if (tid < 32) s_sum->hist[tid] = 0;
+    if (tid < 40) s_dsum[tid] = 0;
     if (stream && staged) {
       // the publisher releases a slot by writing its header after the payload; acquire it across the link (bounded)
       if (tid == 0) {
@@ -419,10 +445,10 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           if (lead) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.err_word), "r"(err) : "memory");   // host-mapped, sticky
         }
       }
-      __syncthreads();
     }
-    const bool aborted = s_sum->abort_launch != 0;
-    if (staged && n && !aborted) {   // peer pull: plain 16-byte loads on the NVLink-mapped pointer, into shared memory and the local copy
+    __syncthreads();
+    const bool ab = s_sum->abort_launch != 0;
+    if (staged && n && !ab) {   // peer pull: plain 16-byte loads on the NVLink-mapped pointer, into shared memory and the local copy
       const uint4* src = reinterpret_cast<const uint4*>(p.batch);
       uint4* loc = reinterpret_cast<uint4*>(p.batch_local);
       uint4* dst = reinterpret_cast<uint4*>(s_batch);
@@ -435,9 +461,9 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     }
     mbar_wait(&s_sum->mbar, 0);
     __syncthreads();
-    if (lead && stream && tid == 0 && !aborted)   // the batch is out of the shared ring: the publisher may reuse the slot
+    if (lead && stream && tid == 0 && !ab)   // the batch is out of the shared ring: the publisher may reuse the slot
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.stream_ack), "l"(p.stream_seq) : "memory");
-    const uint32_t nd = aborted ? 0u : n;
+    const uint32_t nd = ab ? 0u : n;
     {
       uint32_t present = 0, uni = 0;
       for (uint32_t i = tid; i < nd; i += kThreads) {
@@ -446,14 +472,14 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         const uint32_t code = (uint32_t)w.z, target = (uint32_t)w.w;
         uint32_t codebit = 0;
         if (target == CPBUS_TARGET_ALL) {
-          if (code < 32) { codebit = 1u << code; atomicAdd(&s_sum->hist[code], 1u); }
+          if (code < 32) { codebit = 1u << code; atomicAdd(&s_dsum[2 + code], 1u); }
           present |= codebit;
         } else uni = 1;
         s_meta[i] = make_uint2(codebit, target);
       }
       present = __reduce_or_sync(0xffffffffu, present);
       uni = __reduce_or_sync(0xffffffffu, uni);
-      if (lane == 0) { if (present) atomicOr(&s_sum->present, present); if (uni) atomicOr(&s_sum->has_unicast, 1u); }
+      if (lane == 0) { if (present) atomicOr(&s_dsum[0], present); if (uni) atomicOr(&s_dsum[1], 1u); }
     }
     __syncthreads();
     {   // Q: exclusive prefix sums of w_i = H(e_i) P^(n-1-i); Q[n] is the whole batch as one dense run
@@ -476,56 +502,17 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       __syncthreads();
     }
     if (lead) {
-      for (uint32_t i = tid; i < desc_words16; i += kThreads) g_desc[i] = s_desc[i];
-      if (tid < 32) g_sum[2 + tid] = s_sum->hist[tid];
-      if (tid == 0) { g_sum[0] = s_sum->present; g_sum[1] = s_sum->has_unicast; g_sum[34] = s_sum->abort_launch; }
+      for (uint32_t i = tid; i < desc_bytes / 16u; i += kThreads) g_desc[i] = s_desc[i];
       __threadfence();
       __syncthreads();
-      if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(p.launch_seq) : "memory");
-      if (p.acct && !aborted) {   // device-published batch: publish accounting (the other CTAs are already on their way)
-        if (tid < 32 && tid != CPBUS_METRIC && s_sum->hist[tid]) atomicAdd(&p.acct->by_code[tid], (unsigned long long)s_sum->hist[tid]);
-        for (uint32_t i = tid; i < nd; i += kThreads) {
-          if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
-          const uint32_t code = s_batch[i].code;
-          if (code == CPBUS_METRIC || code >= 32u) continue;
-          const unsigned long long key = (((unsigned long long)code << 32) | s_batch[i].source_id) + 1ull;
-          uint32_t slot = pair_key_hash(code, s_batch[i].source_id) & (kAcctPairSlots - 1u);
-          bool placed = false;
-          for (int probe = 0; probe < 256 && !placed; probe++, slot = (slot + 1u) & (kAcctPairSlots - 1u)) {
-            const unsigned long long old = atomicCAS(&p.acct->pair_key[slot], 0ull, key);
-            if (old == 0ull || old == key) { atomicAdd(&p.acct->pair_cnt[slot], 1ull); placed = true; }
-          }
-          if (!placed) atomicAdd(&p.acct->pair_overflow, 1ull);
-        }
-        if (tid == 0) {
-          DevDbgTail* t = &p.acct->tail[p.launch_seq % kAcctDbgRing];
-          uint32_t* idx = s_tick;                                      // warp 0's scratch is free until the main loop
-          uint32_t kept = 0, nb = 0;
-          for (uint32_t c = 0; c < 32; c++) nb += s_sum->hist[c];
-          for (uint32_t i = nd; i > 0 && kept < (uint32_t)kAcctDbgKeep; i--)
-            if (s_meta[i - 1].y == CPBUS_TARGET_ALL) idx[kept++] = i - 1;
-          for (uint32_t j = 0; j < kept; j++) t->ev[j] = s_batch[idx[kept - 1 - j]];
-          t->n_broadcast = nb; t->n_kept = kept;
-          __threadfence();
-          t->launch_seq = p.launch_seq;
-        }
-        __syncthreads();   // idx lives in the per-warp scratch the main loop is about to use
+      if (tid == 0) {
+        const unsigned long long flag = p.launch_seq | (ab ? kAbortBit : 0ull);
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.desc_ready), "l"(flag) : "memory");
       }
     }
   } else {
-    if (tid == 0) s_sum->abort_launch = __ldcg(g_sum + 34);
-    __syncthreads();
-    if (staged && n && tid == 0 && !s_sum->abort_launch) {
-      mbar_wait(&s_sum->mbar, 0);                                    // phase 0 (power table) is over
-      asm volatile("fence.proxy.async;" ::: "memory");               // CTA 0's generic-proxy stores -> our async-proxy read
-      mbar_expect_tx(&s_sum->mbar, n * 32u);
-      bulk_g2s(s_batch, p.batch_local, n * 32u, &s_sum->mbar);
-    }
-    for (uint32_t i = tid; i < desc_words16; i += kThreads) s_desc[i] = __ldcg(g_desc + i);
-    if (tid < 32) s_sum->hist[tid] = __ldcg(g_sum + 2 + tid);
-    if (tid == 0) { s_sum->present = __ldcg(g_sum); s_sum->has_unicast = __ldcg(g_sum + 1); }
+    mbar_wait(&s_sum->mbar_desc, 0);
     mbar_wait(&s_sum->mbar, (staged && n && !s_sum->abort_launch) ? 1u : 0u);
-    __syncthreads();
   }
   const bool aborted = s_sum->abort_launch != 0;   // stream batch missing: this launch delivers nothing and fires no timer
   if (PAIRS) {   // the presence filter sits behind the per-warp scratch (the host adds kPairFilterBytes)
@@ -544,13 +531,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
   const bool timers_on = TIMERS && p.timers_on && K;
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
-  // position space: plain build = subscriber index, strided over the grid; ORDERED build = index into p.order, one
-  // contiguous block of p.spw positions per warp (lane l keeps the id at block position l: one coalesced load)
-  uint32_t pos = ORDERED ? (blockIdx.x * kWarpsPerCta + warp) * p.spw : blockIdx.x * kWarpsPerCta + warp;
   const uint32_t pos_end = aborted ? 0u : (ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs);
   const uint32_t pos_step = ORDERED ? 1u : wstride;
-  uint32_t my_ids = 0;
-  if (ORDERED && pos + lane < pos_end) my_ids = __ldg(p.order + pos + lane);
   const uint32_t pos0 = pos;
   uint32_t s = ORDERED ? __shfl_sync(0xffffffffu, my_ids, 0) : pos;
   // ---- from here on the previous launch's results are needed: wait for it, then let the NEXT launch start its prologue
@@ -562,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     ld_sector(p.ctl + s, ca, cb, keep);
     if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
   }
-  const uint32_t present = s_sum->present;
-  const bool has_unicast = s_sum->has_unicast != 0;
+  const uint32_t present = s_dsum[0];
+  const bool has_unicast = s_dsum[1] != 0;
   const uint32_t Rm = p.ring_cap - 1;
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
   const uint32_t sw = ((uint32_t)lane >> 2) & 1u;                      // which half this lane fetches first (lds_record)
@@ -685,15 +667,23 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       if (tk_valid) my_tick[tk_rank] = tk_pos;
       __syncwarp();
       k = n + n_ticks;
-      // event i lands at i + #{ticks with pos <= i}.  Tick positions are sorted, so the count is warp-uniform for a
-      // whole 32-event chunk unless a tick falls strictly inside it (rare: 2-3 ticks per 256 events in config 3).
-      uint32_t t_idx = 0;
+      // event i lands at i + #{ticks with pos <= i}.  Lane r keeps the r-th smallest tick position in a register, so per
+      // 32-event chunk the count is two ballots and a bit mask — no shared-memory round trip in the copy loop (round 1:
+      // 34 % of this path's stall samples sat on the my_tick[] loads feeding these compares).
+      const uint32_t T = (uint32_t)lane < n_ticks ? my_tick[lane] : 0xFFFFFFFFu;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < n; c0 += 32) {
-        while (t_idx < n_ticks && my_tick[t_idx] <= c0) t_idx++;
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, T <= c0));          // ticks at or in front of the chunk's first event
+        const bool in = T > c0 && T < c0 + 32u;                                        // ... strictly inside the chunk
+        const uint32_t n_in = __popc(__ballot_sync(0xffffffffu, in));
         const uint32_t i = c0 + lane;
-        uint32_t out = i + t_idx;
-        for (uint32_t t = t_idx; t < n_ticks && my_tick[t] < c0 + 32; t++) out += (my_tick[t] <= i) ? 1u : 0u;
+        uint32_t out = i + before;
+        if (n_in) {
+          const uint32_t bits = __reduce_or_sync(0xffffffffu, in ? 1u << (T - c0) : 0u);
+          if (__popc(bits) == n_in) out += __popc(bits & ((2u << lane) - 1u));       // bit d <=> a tick at c0 + d <= i  <=>  d <= lane
+          else                                                                         // several ticks share a position: count them one by one
+            for (uint32_t t = before; t < n_ticks && my_tick[t] < c0 + 32u; t++) out += (my_tick[t] <= i) ? 1u : 0u;
+        }
         if (i < n) {
           uint4 a, b;
           lds_record(s4, i, sw, a, b);
@@ -788,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         __syncwarp();
       } else {
         // timers build: register budget is tighter (80, no spills) — single pass, ballot + running rank
-        uint32_t kk = ((m >> lane) & 1u) ? s_sum->hist[lane] : 0u;
+        uint32_t kk = ((m >> lane) & 1u) ? s_dsum[2 + lane] : 0u;
         kk = __reduce_add_sync(0xffffffffu, kk);
         k = kk;
         uint32_t base = 0;
@@ -930,6 +920,36 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     if (s_sum->acc_ticks) atomicAdd(&rs->ticks, (unsigned long long)s_sum->acc_ticks);
     if (s_sum->acc_dig_lo | s_sum->acc_dig_hi) atomicAdd(&rs->digest_sum, (unsigned long long)s_sum->acc_dig_lo + ((unsigned long long)s_sum->acc_dig_hi << 16));
     if (blockIdx.x == 0) atomicAdd(&rs->launch_seq, p.launch_seq);
+  }
+  if (blockIdx.x == 0 && p.acct && !aborted) {
+    // device-published batch: publish accounting (events/bus.go:128-139), done here — after the lead CTA's own mailboxes —
+    // so that it never delays the fan-out (the staged batch and its descriptor are still intact in shared memory)
+    if (tid < 32 && tid != CPBUS_METRIC && s_dsum[2 + tid]) atomicAdd(&p.acct->by_code[tid], (unsigned long long)s_dsum[2 + tid]);
+    for (uint32_t i = tid; i < n; i += kThreads) {
+      if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
+      const uint32_t code = s_batch[i].code;
+      if (code == CPBUS_METRIC || code >= 32u) continue;
+      const unsigned long long key = (((unsigned long long)code << 32) | s_batch[i].source_id) + 1ull;
+      uint32_t slot = pair_key_hash(code, s_batch[i].source_id) & (kAcctPairSlots - 1u);
+      bool placed = false;
+      for (int probe = 0; probe < 32 && !placed; probe++, slot = (slot + 1u) & (kAcctPairSlots - 1u)) {
+        const unsigned long long old = atomicCAS(&p.acct->pair_key[slot], 0ull, key);
+        if (old == 0ull || old == key) { atomicAdd(&p.acct->pair_cnt[slot], 1ull); placed = true; }
+      }
+      if (!placed) atomicAdd(&p.acct->pair_overflow, 1ull);   // table crowded (> ~10^5 distinct {code, source}): counted, not placed
+    }
+    if (tid == 0) {
+      DevDbgTail* t = &p.acct->tail[p.launch_seq % kAcctDbgRing];
+      uint32_t* idx = s_tick;                                      // every warp of this CTA is past its main loop (barrier above)
+      uint32_t kept = 0, nb = 0;
+      for (uint32_t c = 0; c < 32; c++) nb += s_dsum[2 + c];
+      for (uint32_t i = n; i > 0 && kept < (uint32_t)kAcctDbgKeep; i--)
+        if (s_meta[i - 1].y == CPBUS_TARGET_ALL) idx[kept++] = i - 1;
+      for (uint32_t j = 0; j < kept; j++) t->ev[j] = s_batch[idx[kept - 1 - j]];
+      t->n_broadcast = nb; t->n_kept = kept;
+      __threadfence();
+      t->launch_seq = p.launch_seq;
+    }
   }
   if (blockIdx.x == 0 && p.prefetch_src) {
     // fused ingest: CTA 0 is done with its own mailboxes; pull a LATER batch across NVLink now.  The link round trip

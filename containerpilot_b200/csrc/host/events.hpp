@@ -6,7 +6,9 @@
 //              SetReloadFlag Shutdown Wait DebugEvents)   events/bus.go
 //   EventPublisher / Publisher, EventSubscriber / Subscriber (with a real bounded Rx channel)
 //                                                    events/publisher.go, events/subscriber.go
-//   NewEventTimer / NewEventTimeout(ctx, rx, tick, name)   events/timer.go
+//   NewEventTimer / NewEventTimeout(ctx, rx, tick, name)   events/timer.go — `rx` is ANY channel, as in Go: the Rx of a
+//       subscribed Subscriber (jobs/jobs.go:147-158) or a private channel nobody subscribed (watches/watches.go:37,71);
+//       the latter gets an implicit mailbox with an empty code mask on the current bus (ticks + direct sends only)
 // This is the host side a cgo shim would be (INTEGRATION.md shows the Go version); Go is not
 // installed in this image, so the compiled-language mirror is C++17.  Go panics are `events::Panic`.
 // Every delivery goes through libcpbus (CUDA): mailboxes live in HBM and a pump moves them into `Rx`.
@@ -142,6 +144,7 @@ class Subscriber : public EventSubscriber {   // events/subscriber.go:13-37
   friend void NewEventTimeout(class Context&, const ChanPtr&, std::chrono::nanoseconds, const std::string&);
   friend void NewEventTimer(class Context&, const ChanPtr&, std::chrono::nanoseconds, const std::string&);
   uint32_t id_ = UINT32_MAX;
+  bool implicit_ = false;       // made by the bus for a timer-only channel: not in the WaitGroup, released when Rx is closed
   std::deque<Event> pending_;   // drained from HBM but Rx was full
 };
 
@@ -174,6 +177,13 @@ class Context {
   std::vector<std::function<void()>> hooks_;
 };
 
+namespace detail {
+// which Subscriber (of which bus) owns a channel: kept by Subscribe / Unsubscribe, looked up by the timer functions
+// (Go needs no such table because the timer goroutine writes the channel itself)
+struct RxOwner { EventBus* bus; Subscriber* sub; };
+inline std::map<Chan*, RxOwner>& RxRegistry() { static std::map<Chan*, RxOwner> r; return r; }
+}  // namespace detail
+
 class EventBus {   // events/bus.go:12-22
  public:
   enum class Clock { Virtual, Monotonic };
@@ -187,13 +197,27 @@ class EventBus {   // events/bus.go:12-22
     int rc = cpbus_create(&cfg, &h_);
     if (rc) throw std::runtime_error(std::string("cpbus_create: ") + cpbus_strerror(rc) + " " + cpbus_last_cuda_error());
     start_ = std::chrono::steady_clock::now();
+    life_->h = h_;
+    { std::lock_guard<std::mutex> g(CurrentMutex()); CurrentSlot() = this; }
     if (clock_ == Clock::Monotonic) pump_ = std::thread([this] { PumpLoop(); });
   }
   ~EventBus() {
     stop_ = true;
     if (pump_.joinable()) pump_.join();
+    { std::lock_guard<std::mutex> g(CurrentMutex()); if (CurrentSlot() == this) CurrentSlot() = nullptr; }
+    {
+      std::lock_guard<std::recursive_mutex> l(lock_);
+      life_->alive = false;                       // ctx.OnDone hooks that fire later find a dead bus and do nothing
+      for (auto& kv : registry_) detail::RxRegistry().erase(kv.first->Rx.get());
+    }
     cpbus_destroy(h_);
   }
+  // The bus a bus-less call refers to (NewEventTimer on a channel nobody subscribed): the most recently created live one.
+  // ContainerPilot has exactly one per App run (core/app.go:142).
+  static EventBus* Current() { std::lock_guard<std::mutex> g(CurrentMutex()); return CurrentSlot(); }
+
+  // NewEventTimer / NewEventTimeout (events/timer.go:12-71) for any channel
+  static void StartTimer(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name, int oneshot);
   EventBus(const EventBus&) = delete;
 
   void Register(EventPublisher*) { std::lock_guard<std::recursive_mutex> l(lock_); done_.Add(1); }   // bus.go:91-95
@@ -209,9 +233,21 @@ class EventBus {   // events/bus.go:12-22
     uint32_t id = 0;
     std::vector<cpbus_pair> pairs;
     for (const Event& e : cases) pairs.push_back(cpbus_pair{(uint32_t)e.Code, Intern(e.Source)});
-    Check(cpbus_subscribe_pairs(h_, mask, pairs.data(), (uint32_t)pairs.size(), &id), "cpbus_subscribe_pairs");
+    auto imp = sub->Rx ? implicit_.find(sub->Rx.get()) : implicit_.end();
+    if (imp != implicit_.end() && pairs.empty()) {
+      // the channel already carries timer ticks (NewEventTimer came first): keep that mailbox and its timers, open the mask
+      Subscriber* old = imp->second.get();
+      id = old->id_;
+      Retry([&] { return cpbus_set_mask(h_, id, mask); }, "cpbus_set_mask");
+      sub->pending_ = std::move(old->pending_);
+      registry_.erase(old);
+      implicit_.erase(imp);
+    } else {
+      Retry([&] { return cpbus_subscribe_pairs(h_, mask, pairs.data(), (uint32_t)pairs.size(), &id); }, "cpbus_subscribe_pairs");
+    }
     sub->id_ = id;
     registry_[sub] = id;
+    if (sub->Rx) detail::RxRegistry()[sub->Rx.get()] = {this, sub};
     done_.Add(1);
   }
 
@@ -223,8 +259,9 @@ class EventBus {   // events/bus.go:12-22
     if (it != registry_.end()) {
       FlushLocked();
       DrainOne(sub, /*blocking=*/false);   // what was published before the unsubscribe still reaches Rx
-      Check(cpbus_unsubscribe(h_, it->second), "cpbus_unsubscribe");
+      Retry([&] { return cpbus_unsubscribe(h_, it->second); }, "cpbus_unsubscribe");
       registry_.erase(it);
+      if (sub->Rx) detail::RxRegistry().erase(sub->Rx.get());
       sub->id_ = UINT32_MAX;
     }
     done_.Done();   // negative counter => panic, as sync.WaitGroup does (bus.go:121)
@@ -308,6 +345,47 @@ class EventBus {   // events/bus.go:12-22
     std::mutex m; std::condition_variable cv; long c = 0;
   };
 
+  // state a ctx.OnDone hook may still hold after the bus is gone
+  struct Life { std::recursive_mutex m; bool alive = true; cpbus_t* h = nullptr; };
+  static std::mutex& CurrentMutex() { static std::mutex m; return m; }
+  static EventBus*& CurrentSlot() { static EventBus* b = nullptr; return b; }
+
+  // libcpbus flushes staged events inside membership / timer calls; in lossless mode a full mailbox makes them return
+  // CPBUS_EAGAIN: let the consumers run (drain into Rx) and try again, like a blocked chansend would
+  template <class F>
+  void Retry(F&& call, const char* where) {
+    for (;;) {
+      const int rc = call();
+      if (rc == CPBUS_EAGAIN) { DrainAll(/*blocking=*/true); continue; }
+      Check(rc, where);
+      return;
+    }
+  }
+  // the mailbox behind a channel nobody subscribed (watches/watches.go:37,71): empty code mask, so only ticks and
+  // direct sends land in it; pumped into `rx` like any other; not part of the WaitGroup
+  Subscriber* ImplicitFor(const ChanPtr& rx) {
+    auto it = implicit_.find(rx.get());
+    if (it != implicit_.end()) return it->second.get();
+    auto sub = std::make_unique<Subscriber>();
+    sub->Rx = rx; sub->Bus = this; sub->implicit_ = true;
+    uint32_t id = 0;
+    Retry([&] { return cpbus_subscribe(h_, 0u, &id); }, "cpbus_subscribe");
+    sub->id_ = id;
+    registry_[sub.get()] = id;
+    detail::RxRegistry()[rx.get()] = {this, sub.get()};
+    Subscriber* raw = sub.get();
+    implicit_[rx.get()] = std::move(sub);
+    return raw;
+  }
+  // close(rx) on a timer-only channel: the Go timer goroutine panics on its next send, recovers and exits
+  // (events/timer.go:26-30,50-54) — release the mailbox and with it the timers
+  void ReleaseImplicit(Subscriber* sub) {
+    cpbus_unsubscribe(h_, sub->id_);
+    registry_.erase(sub);
+    detail::RxRegistry().erase(sub->Rx.get());
+    implicit_.erase(sub->Rx.get());
+  }
+
   static void Check(int rc, const char* where) {
     if (rc == CPBUS_ECLOSED) throw Panic("sync: negative WaitGroup counter");
     if (rc) throw std::runtime_error(std::string(where) + ": " + cpbus_strerror(rc) + " " + cpbus_last_cuda_error());
@@ -362,14 +440,21 @@ class EventBus {   // events/bus.go:12-22
         for (uint32_t j = 0; j < drain_cnt_[i]; j++) by_id[i]->pending_.push_back(Event{(EventCode)r[j].code, Source(r[j].source_id)});
       }
     }
+    std::vector<Subscriber*> dead;
     for (auto& kv : registry_) {
       Subscriber* sub = kv.first;
-      while (!sub->pending_.empty() && sub->Rx) {
-        if (blocking) sub->Rx->Send(sub->pending_.front());
-        else if (!sub->Rx->TrySend(sub->pending_.front())) break;
-        sub->pending_.pop_front();
+      try {
+        while (!sub->pending_.empty() && sub->Rx) {
+          if (blocking) sub->Rx->Send(sub->pending_.front());
+          else if (!sub->Rx->TrySend(sub->pending_.front())) break;
+          sub->pending_.pop_front();
+        }
+      } catch (const Panic&) {
+        if (!sub->implicit_) throw;          // bus.go:135-137: publishing into a closed subscriber channel is a panic
+        dead.push_back(sub);                 // timer.go:50-54: the timer goroutine recovers and exits
       }
     }
+    for (Subscriber* sub : dead) ReleaseImplicit(sub);
   }
   void PumpLoop() {
     while (!stop_) {
@@ -387,7 +472,9 @@ class EventBus {   // events/bus.go:12-22
   std::vector<cpbus_event> drain_buf_;
   std::vector<uint32_t> drain_off_, drain_cnt_;
   cpbus_t* h_ = nullptr;
-  std::recursive_mutex lock_;   // bus.lock (bus.go:14): serialises publishers and membership changes
+  std::shared_ptr<Life> life_ = std::make_shared<Life>();
+  std::recursive_mutex& lock_ = life_->m;   // bus.lock (bus.go:14): serialises publishers and membership changes
+  std::map<Chan*, std::unique_ptr<Subscriber>> implicit_;   // timer-only channels
   bool reload_ = false;
   WaitGroup done_;
   std::map<Subscriber*, uint32_t> registry_;   // bus.go:13
@@ -424,33 +511,52 @@ inline void Publisher::Unregister() { Bus->Unregister(this); }                  
 inline void Publisher::Wait() { Bus->Wait(); }                                          // publisher.go:34-36
 
 namespace detail {
-inline std::pair<EventBus*, Subscriber*> OwnerOf(const ChanPtr& rx, std::map<Chan*, Subscriber*>& reg) {
+struct TimerTarget { EventBus* bus; Subscriber* sub; };
+// `rx` is the Rx of a subscribed Subscriber, or any other channel: then the current bus makes it a mailbox of its own
+inline TimerTarget TargetOf(const ChanPtr& rx) {
+  auto& reg = RxRegistry();
   auto it = reg.find(rx.get());
-  if (it == reg.end() || !it->second->Bus) throw Panic("timer rx is not the Rx of a subscribed Subscriber");
-  return {it->second->Bus, it->second};
+  if (it != reg.end() && it->second.sub->Bus) return {it->second.bus, it->second.sub};
+  EventBus* bus = EventBus::Current();
+  if (!bus) throw Panic("NewEventTimer: no EventBus exists in this process");
+  return {bus, nullptr};
 }
-inline std::map<Chan*, Subscriber*>& RxRegistry() { static std::map<Chan*, Subscriber*> r; return r; }
 }  // namespace detail
 
-// Callers pass `rx` exactly as in Go (jobs/jobs.go:147-158, watches/watches.go:71): the Rx of a Subscriber.
-// BindRx records which Subscriber owns a channel (Go needs no such step because the timer writes the channel itself).
-inline void BindRx(Subscriber* sub) { detail::RxRegistry()[sub->Rx.get()] = sub; }
-
-inline void NewEventTimeout(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name) {   // timer.go:12-37
-  auto [bus, sub] = detail::OwnerOf(rx, detail::RxRegistry());
+inline void EventBus::StartTimer(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name, int oneshot) {
+  if (rx->Closed()) return;   // the goroutine's first send would panic and be recovered: no tick ever arrives
+  detail::TimerTarget t = detail::TargetOf(rx);
+  EventBus* bus = t.bus;
   std::lock_guard<std::recursive_mutex> l(bus->lock_);
+  Subscriber* sub = t.sub ? t.sub : bus->ImplicitFor(rx);
   uint32_t tid = 0;
-  EventBus::Check(cpbus_timer_add(bus->h_, sub->id_, (uint64_t)tick.count(), bus->Intern(name), 1, &tid), "cpbus_timer_add");
-  cpbus_t* h = bus->h_; std::recursive_mutex* m = &bus->lock_;
-  ctx.OnDone([h, m, tid] { std::lock_guard<std::recursive_mutex> g(*m); cpbus_timer_cancel(h, tid); });   // ctx.Done(): timer.go:20-22
+  const uint32_t src = bus->Intern(name);
+  bus->Retry([&] { return cpbus_timer_add(bus->h_, sub->id_, (uint64_t)tick.count(), src, oneshot, &tid); }, "cpbus_timer_add");
+  // ctx.Done() (timer.go:20-22,57-58).  The hook may outlive the bus: it holds the bus's Life, not the bus.  Timer ids
+  // carry a generation, so a late cancel can never disarm a slot that has been re-armed since.
+  std::shared_ptr<Life> life = bus->life_;
+  ctx.OnDone([life, bus, tid] {
+    std::lock_guard<std::recursive_mutex> g(life->m);
+    if (!life->alive) return;
+    for (;;) {
+      const int rc = cpbus_timer_cancel(life->h, tid);
+      if (rc != CPBUS_EAGAIN) break;          // ENOENT: already fired / gone
+      bus->DrainAll(/*blocking=*/true);       // a full mailbox held back the flush in front of the cancel: let consumers run
+    }
+  });
+}
+namespace detail {
+inline void StartTimer(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name, int oneshot) {
+  EventBus::StartTimer(ctx, rx, tick, name, oneshot);
+}
+}  // namespace detail
+
+// Callers pass `rx` exactly as in Go (jobs/jobs.go:147-158, watches/watches.go:71): any `chan Event`.
+inline void NewEventTimeout(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name) {   // timer.go:12-37
+  detail::StartTimer(ctx, rx, tick, name, 1);
 }
 inline void NewEventTimer(Context& ctx, const ChanPtr& rx, std::chrono::nanoseconds tick, const std::string& name) {     // timer.go:40-71
-  auto [bus, sub] = detail::OwnerOf(rx, detail::RxRegistry());
-  std::lock_guard<std::recursive_mutex> l(bus->lock_);
-  uint32_t tid = 0;
-  EventBus::Check(cpbus_timer_add(bus->h_, sub->id_, (uint64_t)tick.count(), bus->Intern(name), 0, &tid), "cpbus_timer_add");
-  cpbus_t* h = bus->h_; std::recursive_mutex* m = &bus->lock_;
-  ctx.OnDone([h, m, tid] { std::lock_guard<std::recursive_mutex> g(*m); cpbus_timer_cancel(h, tid); });   // ctx.Done(): timer.go:57-58
+  detail::StartTimer(ctx, rx, tick, name, 0);
 }
 
 }  // namespace events

@@ -156,7 +156,6 @@ static void TestTimers() {
   Subscriber job, other;
   job.Rx = MakeChan(1000); other.Rx = MakeChan(1000);
   job.Subscribe(&bus); other.Subscribe(&bus);
-  BindRx(&job);
   Context ctx;
   using namespace std::chrono_literals;
   NewEventTimer(ctx, job.Rx, 1s, "myjob.heartbeat");
@@ -178,6 +177,100 @@ static void TestTimers() {
   while (job.Rx->Recv(&e)) got.push_back(e);
   EXPECT((got == std::vector<Event>{GlobalShutdown}));
   EXPECT((bus.DebugEvents() == std::vector<Event>{GlobalStartup, Event{StatusHealthy, "myjob"}, GlobalShutdown}));
+}
+
+// watches/watches.go:65-101 as an actor on the mirror: the Watch keeps a PRIVATE channel that is never subscribed
+// (watches.go:37), hands it to NewEventTimer (watches.go:71) and publishes Status* events when the backend reports a change.
+struct NoopDiscoveryBackend {   // tests/mocks/discovery.go:6-22
+  bool Val = false, lastVal = false;
+  std::pair<bool, bool> CheckForUpstreamChanges() { bool changed = lastVal != Val; lastVal = Val; return {changed, Val}; }
+};
+struct Watch : Publisher {
+  std::string Name; ChanPtr rx = MakeChan(1000); NoopDiscoveryBackend disc; Context ctx; std::thread th; std::string timerSource;
+  void Run(EventBus* bus, std::chrono::nanoseconds poll) {   // watches.go:65-96
+    Register(bus);
+    timerSource = Name + ".poll";
+    NewEventTimer(ctx, rx, poll, timerSource);   // any `chan Event`: this one is not a bus subscriber
+    th = std::thread([this] {
+      for (;;) {
+        Event e;
+        if (!rx->Recv(&e, std::chrono::milliseconds(2))) { if (ctx.Done()) break; continue; }
+        if (e == QuitByTest) break;
+        if (e == Event{TimerExpired, timerSource}) {
+          auto [didChange, isHealthy] = disc.CheckForUpstreamChanges();
+          if (didChange) {
+            Publish(Event{StatusChanged, Name});
+            Publish(Event{isHealthy ? StatusHealthy : StatusUnhealthy, Name});
+          }
+        }
+      }
+      ctx.Cancel(); Unregister();
+    });
+  }
+  void Receive(const Event& e) { rx->Send(e); }   // watches.go:99-101: `watch.rx <- event`
+};
+
+// watches/watches_test.go:13-58
+static std::map<Event, int> RunWatchTest(const std::string& name, bool val) {
+  EventBus bus(EventBus::Clock::Monotonic);
+  Watch watch; watch.Name = "watch." + name; watch.disc.Val = val;
+  watch.Run(&bus, std::chrono::seconds(1));
+  Event poll{TimerExpired, watch.Name + ".poll"};
+  watch.Receive(poll);
+  watch.Receive(poll);   // "Ensure we can run it more than once"
+  watch.Receive(QuitByTest);
+  watch.th.join();
+  bus.Wait();
+  std::map<Event, int> got;
+  for (auto& e : bus.DebugEvents()) got[e]++;
+  return got;
+}
+static void TestWatchPoll() {
+  std::printf("TestWatchPoll\n");
+  auto ok = RunWatchTest("mywatchOk", true);
+  EXPECT((ok[Event{StatusChanged, "watch.mywatchOk"}] == 1 && ok[Event{StatusHealthy, "watch.mywatchOk"}] == 1));
+  auto fail = RunWatchTest("mywatchFail", false);
+  EXPECT((fail[Event{StatusChanged, "watch.mywatchFail"}] == 0 && fail[Event{StatusUnhealthy, "watch.mywatchFail"}] == 0));
+}
+
+// events/timer.go:40-71 on a channel nobody subscribed: real ticks under the virtual clock, interleaved with direct sends;
+// broadcasts never land there; a late Subscribe keeps the mailbox; closing the channel ends the timer (timer.go:50-54)
+static void TestTimerOnPrivateChannel() {
+  std::printf("TestTimerOnPrivateChannel\n");
+  EventBus bus(EventBus::Clock::Virtual);
+  Subscriber other; other.Rx = MakeChan(1000); other.Subscribe(&bus);
+  ChanPtr rx = MakeChan(1000);
+  Context ctx;
+  using namespace std::chrono_literals;
+  NewEventTimer(ctx, rx, 1000ns, "w.poll");
+  NewEventTimeout(ctx, rx, 2500ns, "w.once");
+  bus.Advance(1000);
+  bus.Publish(Event{Startup, "everyone"});
+  bus.Advance(3000);
+  Event tick{TimerExpired, "w.poll"}, once{TimerExpired, "w.once"}, e;
+  std::vector<Event> got, got2;
+  while (rx->Recv(&e)) got.push_back(e);
+  while (other.Rx->Recv(&e)) got2.push_back(e);
+  EXPECT((got == std::vector<Event>{tick, tick, once, tick}));
+  EXPECT((got2 == std::vector<Event>{Event{Startup, "everyone"}}));
+  ctx.Cancel();
+  bus.Advance(6000);
+  EXPECT(!rx->Recv(&e));
+  Context ctx2;
+  NewEventTimer(ctx2, rx, 1000ns, "w.again");
+  Subscriber late; late.Rx = rx; late.Subscribe(&bus);   // the channel becomes a real subscriber: mailbox and timer are kept
+  bus.Advance(7000);
+  bus.Publish(Event{Signal, "SIGHUP"});
+  got.clear();
+  while (rx->Recv(&e)) got.push_back(e);
+  EXPECT((got == std::vector<Event>{Event{TimerExpired, "w.again"}, Event{Signal, "SIGHUP"}}));
+  ChanPtr rx2 = MakeChan(10);
+  NewEventTimer(ctx2, rx2, 1000ns, "w.closed");
+  rx2->Close();
+  bus.Advance(9000);   // the tick meets a closed channel: the implicit mailbox is released, nothing panics
+  bus.Advance(10000);
+  ctx2.Cancel();
+  late.Unsubscribe(); other.Unsubscribe();
 }
 
 // events/events.go:52-86 and eventcode_string.go:9-15
@@ -267,6 +360,8 @@ int main() {
   TestPostMetricMultiset();
   TestPanics();
   TestTimers();
+  TestWatchPoll();
+  TestTimerOnPrivateChannel();
   TestConfig1Plumbing();
   TestManySubscribers();
   TestSubscribeWithCases();

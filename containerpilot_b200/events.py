@@ -10,6 +10,12 @@ Same names, argument meaning and error behaviour as the Go API
     Publisher / Subscriber (+ Rx)                      events/publisher.go, subscriber.go
     NewEventTimer / NewEventTimeout                    events/timer.go
 
+`NewEventTimer` / `NewEventTimeout` take any `Chan`, exactly as the Go functions take any `chan Event`
+(events/timer.go:12-16,40-45): when the channel is not the Rx of a subscribed Subscriber (a Watch's private channel,
+watches/watches.go:37,71) the bus gives it a mailbox of its own — an implicit subscriber with an empty code mask that
+receives only the ticks and direct sends — on the bus most recently created in this process (the reference has exactly
+one live bus per App run, core/app.go:142).
+
 Differences, all forced by running under a virtual clock in tests:
   * `Rx` is a `Chan` whose receive side drains the subscriber's HBM mailbox
     (`cpbus_drain`) — in the Go shim a drain goroutine pumps a real `chan Event`;
@@ -20,6 +26,7 @@ Every delivery goes through libcpbus (CUDA).  There is no CPU data path here.
 """
 from __future__ import annotations
 
+import weakref
 from collections import deque
 from dataclasses import dataclass
 
@@ -80,7 +87,12 @@ class Chan:
         self._sub = None            # owning Subscriber once subscribed
 
     def close(self):
+        """close(rx).  A timer goroutine that then sends into it panics, recovers and exits (events/timer.go:26-30,
+        50-54): the implicit mailbox behind a timer-only channel is released, and with it its timers."""
         self.closed = True
+        sub = self._sub
+        if sub is not None and getattr(sub, "_implicit", False) and sub.Bus is not None and sub._id is not None:
+            sub.Bus._release_implicit(sub)
 
     def send(self, event: Event):
         """`rx <- event`: direct mailbox write (jobs/jobs.go:262)."""
@@ -112,6 +124,8 @@ class EventBus:
         self.reload = False
         self._done = 0              # sync.WaitGroup counter (bus.go:16)
         self._subs = {}             # Subscriber -> sub_id  (registry, bus.go:13)
+        self._implicit = {}         # Chan -> implicit Subscriber (timer-only channels; NOT in the registry or the WaitGroup)
+        _live_buses.append(weakref.ref(self))
 
     # ---- lifecycle accounting ----
     def Register(self, publisher):          # bus.go:91-95
@@ -126,10 +140,17 @@ class EventBus:
         """`cases`: exact Event values of the consumer's switch (jobs/jobs.go:197-231) delivered on top of `mask`"""
         if not isinstance(subscriber, Subscriber):
             raise BusPanic("interface conversion: EventSubscriber is not *Subscriber")
-        if cases:
+        imp = self._implicit.pop(subscriber.Rx, None) if subscriber.Rx is not None else None
+        if imp is not None and not cases:
+            # the channel already carries timer ticks (NewEventTimer came first): keep that mailbox and its timers, open the mask
+            self._bus.set_mask(imp._id, mask)
+            subscriber._id, subscriber._tail = imp._id, imp._tail
+        elif cases:
             subscriber._id = self._bus.subscribe_pairs(mask, [(e.Code, self._bus.intern(e.Source)) for e in cases])
         else:
             subscriber._id = self._bus.subscribe(mask)
+        if subscriber.Rx is not None:
+            subscriber.Rx._sub = subscriber
         self._subs[subscriber] = subscriber._id
         self._done += 1
 
@@ -207,8 +228,40 @@ class EventBus:
         recs = self._bus.drain(sub._id)
         return [Event(int(r["code"]), self._bus.source(int(r["source_id"]))) for r in recs]
 
+    # ---- timer-only channels ----
+    def _implicit_for(self, rx: "Chan"):
+        sub = self._implicit.get(rx)
+        if sub is None:
+            sub = Subscriber(rx)
+            sub.Bus, sub._implicit = self, True
+            sub._id = self._bus.subscribe(0)          # empty mask: broadcasts never land here, ticks and direct sends do
+            self._implicit[rx] = sub
+        return sub
+
+    def _release_implicit(self, sub):
+        self._implicit.pop(sub.Rx, None)
+        try:
+            self._bus.unsubscribe(sub._id)            # disarms its timers too
+        except nat.CpbusError:
+            pass
+        sub._id = None
+
     def close(self):
         self._bus.close()
+        _live_buses[:] = [r for r in _live_buses if r() is not None and r() is not self]
+
+
+_live_buses: list = []
+
+
+def _current_bus() -> EventBus:
+    """The bus a bus-less call (`NewEventTimer(ctx, rx, ...)` on an unsubscribed channel) refers to: the most recently
+    created live one.  ContainerPilot has exactly one per App run (core/app.go:142)."""
+    for r in reversed(_live_buses):
+        b = r()
+        if b is not None and b._bus._h:
+            return b
+    raise BusPanic("NewEventTimer: no EventBus exists in this process")
 
 
 NewEventBus = EventBus
@@ -242,6 +295,7 @@ class Subscriber:
         self.Bus = None
         self._id = None
         self._tail = []
+        self._implicit = False      # True: the bus made this mailbox for a timer-only channel (NewEventTimer on an unsubscribed rx)
         if rx is not None:
             rx._sub = self
 
@@ -299,7 +353,11 @@ def WithCancel():
 def _new_timer(ctx: Context, rx: Chan, tick_ns: int, name: str, oneshot: bool):
     sub = rx._sub
     if sub is None or sub.Bus is None or sub._id is None:
-        raise BusPanic("timer rx is not a subscribed mailbox")
+        # any `chan Event` will do (events/timer.go:40-46 takes only ctx, rx, tick, name): a Watch passes a private
+        # channel that is not a bus subscriber (watches/watches.go:37,71)
+        if rx.closed:
+            return                              # the goroutine's first send would panic and be recovered: no tick ever arrives
+        sub = _current_bus()._implicit_for(rx)
     bus = sub.Bus
     tid = bus._bus.timer_add(sub._id, tick_ns, bus._bus.intern(name), oneshot)
     ctx._timers.append((bus, tid))

@@ -166,10 +166,15 @@ int cpbus_subscribe_pairs(cpbus_t* bus, uint32_t code_mask, const cpbus_pair* pa
 int cpbus_subscribe_pairs_many(cpbus_t* bus, const uint32_t* code_masks, const cpbus_pair* pairs, const uint32_t* n_pairs,
                                uint32_t n, uint32_t* first_sub_id);
 int cpbus_unsubscribe(cpbus_t* bus, uint32_t sub_id);
+/* Change a subscriber's code mask in place (ordered with publishes).  Mailbox, timers and exact cases are kept.  The
+ * shims use it when a channel that only carried timer ticks (implicit mask-0 subscriber, see NewEventTimer in
+ * INTEGRATION.md) is subscribed to the bus afterwards. */
+int cpbus_set_mask(cpbus_t* bus, uint32_t sub_id, uint32_t code_mask);
 
 /* ---- timers: NewEventTimer / NewEventTimeout (events/timer.go:40-71 / 12-37).
  *      The first firing is due at now + period_ns; a periodic timer then fires
- *      every period_ns, a one-shot exactly once.  cancel = ctx.Done(). ---- */
+ *      every period_ns, a one-shot exactly once.  cancel = ctx.Done().  A timer id carries a generation: cancelling an
+ *      id whose slot has fired (one-shot) or been re-armed since returns CPBUS_ENOENT and touches nothing. ---- */
 int cpbus_timer_add(cpbus_t* bus, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id);
 /* one periodic timer per subscriber [first_sub, first_sub+n); source_ids[i] (or source_id0+i if NULL) */
 int cpbus_timer_add_many(cpbus_t* bus, uint32_t first_sub, uint32_t n, uint64_t period_ns, const uint32_t* source_ids, uint32_t source_id0, int oneshot);

@@ -197,3 +197,149 @@ def test_post_metric_burst_is_one_fan_out():
         assert s.Received() == want
         s.Unsubscribe()
     bus.close()
+
+
+# ---- watches/watches.go:65-101 restated as an actor on the mirror: a Watch keeps a PRIVATE channel that is not a bus
+#      subscriber (watches.go:37), hands it to NewEventTimer (watches.go:71) and publishes Status* events on change ----
+class Watch(events.Publisher):
+    __test__ = False
+
+    def __init__(self, name, poll_ns, backend):
+        super().__init__()
+        self.Name, self.poll_ns, self.backend = "watch." + name, poll_ns, backend
+        self.rx = events.Chan(1000)                  # watches.go:39 — never passed to bus.Subscribe
+        self.done = False
+
+    def Run(self, pctx, bus):                        # watches.go:65-96
+        self.Register(bus)
+        self.ctx, self.cancel = events.WithCancel()
+        self.timerSource = self.Name + ".poll"
+        events.NewEventTimer(self.ctx, self.rx, self.poll_ns, self.timerSource)
+
+    def Receive(self, event):                        # watches.go:99-101: `watch.rx <- event`
+        self.rx.send(event)
+
+    def pump(self):
+        """the goroutine body of watches.go:73-95, run on demand (one pass over what the channel holds)"""
+        for event in self.rx.recv_all():
+            if self.done:
+                break
+            if event == events.QuitByTest:
+                self.cancel(); self.Unregister(); self.done = True
+                break
+            if event == Event(events.TimerExpired, self.timerSource):
+                changed, healthy = self.backend.check()
+                if changed:
+                    self.Publish(Event(events.StatusChanged, self.Name))
+                    self.Publish(Event(events.StatusHealthy if healthy else events.StatusUnhealthy, self.Name))
+
+
+class NoopDiscoveryBackend:                          # tests/mocks/discovery.go:6-22
+    def __init__(self, val):
+        self.Val, self.lastVal = val, False
+
+    def check(self):
+        changed = self.lastVal != self.Val
+        self.lastVal = self.Val
+        return changed, self.Val
+
+
+def _run_watch_test(name, val):                      # watches/watches_test.go:41-58
+    bus = events.NewEventBus()
+    watch = Watch(name, 1_000_000_000, NoopDiscoveryBackend(val))
+    watch.Run(None, bus)
+    poll = Event(events.TimerExpired, watch.Name + ".poll")
+    watch.Receive(poll)
+    watch.Receive(poll)                              # "Ensure we can run it more than once"
+    watch.Receive(events.QuitByTest)
+    watch.pump()
+    assert bus.Wait() is False
+    got = {}
+    for e in bus.DebugEvents():
+        got[e] = got.get(e, 0) + 1
+    bus.close()
+    return got
+
+
+def test_watch_poll_ok():
+    """watches/watches_test.go:13-26"""
+    got = _run_watch_test("mywatchOk", True)
+    assert got.get(Event(events.StatusChanged, "watch.mywatchOk"), 0) == 1
+    assert got.get(Event(events.StatusHealthy, "watch.mywatchOk"), 0) == 1
+
+
+def test_watch_poll_fail():
+    """watches/watches_test.go:28-39"""
+    got = _run_watch_test("mywatchFail", False)
+    assert got.get(Event(events.StatusChanged, "watch.mywatchFail"), 0) == 0
+    assert got.get(Event(events.StatusUnhealthy, "watch.mywatchFail"), 0) == 0
+
+
+def test_timer_on_a_channel_that_is_not_a_subscriber():
+    """events/timer.go:40-71 takes any `chan Event`: the real ticker of a Watch (watches.go:71) fires into its private
+    channel, interleaved in order with direct sends; broadcasts never land there; closing the channel ends the timer
+    (timer.go:50-54: the goroutine recovers from the send on a closed channel and exits)."""
+    bus = events.NewEventBus()
+    other = TestSubscriber(); other.Run(bus)
+    rx = events.Chan(1000)
+    ctx, cancel = events.WithCancel()
+    events.NewEventTimer(ctx, rx, 1000, "w.poll")
+    events.NewEventTimeout(ctx, rx, 2500, "w.once")
+    bus.Advance(1000)
+    rx.send(Event(events.Quit, "direct"))
+    bus.Publish(Event(events.Startup, "everyone"))   # a broadcast: must not reach the timer-only channel
+    bus.Advance(3000)
+    tick, once = Event(events.TimerExpired, "w.poll"), Event(events.TimerExpired, "w.once")
+    assert rx.recv_all() == [tick, Event(events.Quit, "direct"), tick, once, tick]
+    assert other.Received() == [Event(events.Startup, "everyone")]
+    assert bus.Wait.__self__._done == 1              # the implicit mailbox is not in the WaitGroup (only `other` is)
+    cancel()
+    bus.Advance(5000)
+    assert rx.recv_all() == []
+    # subscribing the same channel afterwards keeps the mailbox (and opens the mask)
+    ctx2, cancel2 = events.WithCancel()
+    events.NewEventTimer(ctx2, rx, 1000, "w.again")
+    late = events.Subscriber(rx)
+    late.Subscribe(bus)
+    bus.Advance(6000)
+    bus.Publish(Event(events.Signal, "SIGHUP"))
+    assert late.Received() == [Event(events.TimerExpired, "w.again"), Event(events.Signal, "SIGHUP")]
+    rx2 = events.Chan(10)
+    events.NewEventTimer(ctx2, rx2, 1000, "w.closed")
+    rx2.close()                                      # timer goroutine would panic on its next send, recover and exit
+    bus.Advance(9000)
+    assert bus._bus.stats()["n_timers"] == 1         # only "w.again" is still armed
+    cancel2()
+    late.Unsubscribe(); other.Stop()
+    bus.close()
+
+
+def test_masks_derived_from_the_switches_run_on_the_cuda_bus():
+    """N1 on hardware: subscribe with masks.job_mask() / METRIC_MASK through the CUDA bus and check that every event the
+    consumer's switch would have handled is still delivered, in order (jobs/jobs.go:195-233, telemetry/metrics.go:97-106)."""
+    import numpy as np
+    from containerpilot_b200 import masks
+    bus = events.NewEventBus(n_max_subs=16)
+    sw = masks.JobSwitch("myjob", start_event=Event(events.StatusHealthy, "watch.db"), health_check_name="check.myjob",
+                         stopping_wait_event=Event(events.Stopped, "db"), has_stopping_timeout=True)
+    job_all, job_masked, job_exact, metric = (events.Subscriber(events.Chan()) for _ in range(4))
+    job_all.Subscribe(bus)
+    job_masked.Subscribe(bus, sw.mask())
+    job_exact.Subscribe(bus, *sw.cases())                  # 17 cases: the one that does not fit widens the mask
+    metric.Subscribe(bus, masks.METRIC_MASK)
+    rng = np.random.default_rng(3)
+    sources = ["myjob", "check.myjob", "myjob.run-every", "myjob.stopping-timeout", "watch.db", "db", "global", "closed",
+               "SIGHUP", "SIGUSR2", "other", "m|1"]
+    for _ in range(800):
+        bus.Publish(Event(int(rng.integers(0, 17)), sources[int(rng.integers(0, len(sources)))]))
+    full = job_all.Received()
+    handled = [e for e in full if sw.handles(e)]
+    assert Event(events.Stopping, "myjob.stopping-timeout") in handled
+    assert [e for e in job_masked.Received() if sw.handles(e)] == handled and len(handled) > 0   # nothing the switch handles is lost, order kept
+    assert [e for e in job_exact.Received() if sw.handles(e)] == handled
+    ms = masks.MetricSwitch()
+    assert [e for e in metric.Received() if ms.handles(e)] == [e for e in full if ms.handles(e)]
+    job_exact.Unsubscribe()
+    for s_ in (job_all, job_masked, metric):
+        s_.Unsubscribe()
+    bus.close()
