@@ -484,6 +484,81 @@ def run_config(cx, name: str, headline: bool):
     return res
 
 
+def run_lossless_and_bridge(cx):
+    """Two records beside the throughput-mode numbers (N = 1):
+    * config 2's shape in LOSSLESS mode — the reference's only semantics (`sub.Rx <- event` blocks on a full channel,
+      events/subscriber.go:30-32) — through the host API (cpbus_advance + cpbus_publish + cpbus_flush) with a device-side
+      consumer (cpbus_consume_all) that keeps up, so no flush has to be refused;
+    * the mailbox -> host bridge (cpbus_drain_many: one gather kernel + two D2H copies into pinned memory), records/s."""
+    import torch
+    import oracle_binding as ob
+    from containerpilot_b200 import _native as nat
+    from containerpilot_b200.bus import Bus, EVENT_DTYPE
+    args, local, stream = cx.args, cx.local, cx.stream
+    n_subs, B, R = 65_536, args.batch, args.ring
+    steps = args.steps or 2000
+    warmup = max(args.warmup, 3)
+    rng = np.random.default_rng(0xC0DEB2A1)
+    n_host = 256
+    host = np.zeros(n_host * B, dtype=EVENT_DTYPE)
+    host["code"] = rng.integers(1, 17, n_host * B); host["source_id"] = rng.integers(0, 4096, n_host * B)
+    bus = Bus(n_subs, ring_cap=R, batch_cap=B, lossless=True, digest=True, device=local, stream=stream.cuda_stream)
+    bus.subscribe_many(np.full(n_subs, nat.MASK_ALL, dtype=np.uint32))
+    orc = ob.Oracle(1, keep_window=8); orc.subscribe()
+    step = [0]
+
+    def go(k):
+        for _ in range(k):
+            i = step[0]
+            lo = (i % n_host) * B
+            nat.check(bus.advance((i + 1) * B * DT_NS), "cpbus_advance")
+            nat.check(bus.publish_many(host[lo:lo + B]), "cpbus_publish")
+            nat.check(bus.flush(), "cpbus_flush")                # never EAGAIN: the consumer keeps up
+            bus.consume_all()
+            step[0] = i + 1
+    go(warmup); torch.cuda.synchronize()
+    s0 = bus.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(stream); go(steps); e1.record(stream)
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)
+    s1 = bus.stats()
+    for i in range(step[0]):                                     # the delivered sequence is the same as in throughput mode
+        lo = (i % n_host) * B
+        orc.advance((i + 1) * B * DT_NS)
+        orc.publish_many(host["code"][lo:lo + B], host["source_id"][lo:lo + B])
+    dg = bus.digests(0, n_subs)
+    ok = bool((dg["count"] == orc.count(0)).all() and (dg["digest"] == orc.digest(0)).all() and s1["overwritten"] == 0)
+    deliveries = s1["deliveries"] - s0["deliveries"]
+    lossless = {"name": "config2-lossless", "workload": "config 2's shape in lossless mode (reference semantics) with a device consumer that keeps up",
+                "value": deliveries / (ms * 1e-3), "unit": "deliveries/s", "steps": steps, "ms_per_step": ms / steps,
+                "api": "cpbus_advance + cpbus_publish(host events) + cpbus_flush + cpbus_consume_all per step, host buffers",
+                "admit_passes": s1["admit_passes"] - s0["admit_passes"], "admit_skipped": s1["admit_skipped"] - s0["admit_skipped"],
+                "parity_checked": ok, "config": {"subscribers_per_gpu": n_subs, "events_per_step": B, "ring_cap": R, "mode": "lossless"}}
+    # ---- bridge: what moving mailboxes back to host channels costs (the shim's pump, INTEGRATION.md §4) ----
+    n_drain = 8192
+    pinned = torch.empty((n_drain * B, 32), dtype=torch.uint8).pin_memory()
+    out = pinned.numpy().view(EVENT_DTYPE).reshape(-1)
+    times, total = [], 0
+    for rep in range(4):
+        i = step[0]
+        nat.check(bus.advance((i + 1) * B * DT_NS), "cpbus_advance")
+        nat.check(bus.publish_many(host[:B]), "cpbus_publish"); nat.check(bus.flush(), "cpbus_flush"); bus.sync()
+        step[0] = i + 1
+        t0 = time.perf_counter()
+        _, offs, cnts = bus.drain_many(0, n_drain, n_drain * B, out=out)
+        dt = time.perf_counter() - t0
+        if rep:                                                  # first call allocates the device staging
+            times.append(dt); total = int(cnts.sum())
+        bus.consume_all()
+    med = float(np.median(times))
+    bridge = {"name": "bridge", "workload": f"cpbus_drain_many: {n_drain} mailboxes x {B} records -> pinned host memory (one gather kernel + two D2H copies)",
+              "value": total / med, "unit": "records/s", "gb_per_s": total * 32 / med / 1e9, "ms_per_call": med * 1e3, "records_per_call": total}
+    bus.close()
+    return lossless, bridge
+
+
 def verify(cx, name, sb, log, base, masks, n_subs, B, K_timers, timer_src0, slot_hist, make_records):
     """After the timed regions: (1) sampled subscribers of this shard — count, order-sensitive digest and the last-1024
     window — against a 1-subscriber oracle placed at that global id and fed the exact batches the bench issued; (2) the
@@ -578,6 +653,11 @@ def main():
         names = names[:1]
     results = [run_config(cx, n, headline=(i == 0)) for i, n in enumerate(names)]
     ok = all(r["parity_checked"] for r in results) or args.no_verify
+    side = []
+    if cx.world == 1 and args.workload == "default" and not args.no_extras:
+        lossless, bridge = run_lossless_and_bridge(cx)
+        side = [lossless, bridge]
+        ok = ok and lossless["parity_checked"]
     if cx.rank == 0:
         h = results[0]
         line = {
@@ -589,7 +669,7 @@ def main():
             "gpu_launches_e2e": h["gpu_launches_e2e"], "clocks": h["clocks"], "parity_checked": h["parity_checked"], "parity": h["parity"],
             "extra_configs": [{k: r[k] for k in ("name", "workload", "scaling", "steps", "value", "unit", "ms_per_step", "publishes_per_s", "deliveries",
                                                   "ticks", "config", "roofline", "e2e", "gpu_launches", "clocks", "parity_checked", "parity")}
-                              for r in results[1:]],
+                              for r in results[1:]] + side,
         }
         print(json.dumps(line), flush=True)
     if cx.world > 1:

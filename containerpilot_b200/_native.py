@@ -49,7 +49,8 @@ class Stats(C.Structure):
                 ("batches", C.c_uint64), ("kernel_launches", C.c_uint64), ("overwritten", C.c_uint64),
                 ("published_by_code", C.c_uint64 * N_CODES), ("n_subs", C.c_uint32), ("n_timers", C.c_uint32),
                 ("now_ns", C.c_uint64), ("intern_entries", C.c_uint64), ("intern_bytes", C.c_uint64),
-                ("ephemeral_live", C.c_uint64), ("ephemeral_recycled", C.c_uint64)]
+                ("ephemeral_live", C.c_uint64), ("ephemeral_recycled", C.c_uint64),
+                ("admit_passes", C.c_uint64), ("admit_skipped", C.c_uint64)]
 
 
 class PairCount(C.Structure):
@@ -95,6 +96,7 @@ SYMBOLS = {
     "cpbus_shared_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpbus_drain": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, _P(C.c_size_t), _P(C.c_uint64)]),
     "cpbus_drain_many": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, _P(C.c_size_t)]),
+    "cpbus_consume_all": (C.c_int, [C.c_void_p]),
     "cpbus_peek_window": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_digest": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "cpbus_digest_fold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64 * 4)]),

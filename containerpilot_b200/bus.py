@@ -215,9 +215,15 @@ class Bus:
         nat.check(self._lib.cpbus_drain(self._h, sub_id, out.ctypes.data, cap, C.byref(n), C.byref(lost)), "cpbus_drain")
         return out[: n.value]
 
-    def drain_many(self, first_sub: int, n: int, cap: int):
-        """Bulk drain: returns (records, offsets, counts); mailbox i's FIFO run is records[offsets[i]:offsets[i]+counts[i]]."""
-        out = np.zeros(cap, dtype=EVENT_DTYPE)
+    def consume_all(self):
+        """device-side consumer: every mailbox read to the end, records discarded"""
+        nat.check(self._lib.cpbus_consume_all(self._h), "cpbus_consume_all")
+
+    def drain_many(self, first_sub: int, n: int, cap: int, out=None):
+        """Bulk drain: returns (records, offsets, counts); mailbox i's FIFO run is records[offsets[i]:offsets[i]+counts[i]].
+        `out`: a preallocated EVENT_DTYPE array of at least `cap` records (pinned memory makes the D2H a straight DMA)."""
+        if out is None:
+            out = np.zeros(cap, dtype=EVENT_DTYPE)
         offs, cnts = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
         total = C.c_size_t()
         nat.check(self._lib.cpbus_drain_many(self._h, first_sub, n, out.ctypes.data, cap, offs.ctypes.data, cnts.ctypes.data,

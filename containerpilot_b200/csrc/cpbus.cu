@@ -133,6 +133,10 @@ struct cpbus {
 
   // clock and ordinals
   uint64_t now = 0, last_watermark = 0, seq = 0;
+  // lossless mode: a lower bound of the free slots of the FULLEST mailbox.  While a batch provably fits (bound >= what it
+  // can append to one mailbox) the admission pass and its host sync are skipped; the bound is refreshed exactly whenever
+  // the admission kernel does run, and reset by cpbus_consume_all.
+  uint64_t room_lb = 0;
 
   // DebugEvents ring (events/bus.go:18-21, 24-54)
   int dbg_head = -1, dbg_tail = 0;
@@ -320,21 +324,32 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
   return CPBUS_OK;
 }
 
-// lossless admission (reference: the sender blocks on a full channel)
+// lossless admission (reference: the sender blocks on a full channel, events/subscriber.go:30-32)
 int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) {
   *ok = true;
   if (!b->lossless || b->n_next == 0) return CPBUS_OK;
-  CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, sizeof(unsigned long long), b->stream));
+  // the most this launch can append to ONE mailbox: every event of the batch + every firing of its timer slots in the window
+  uint64_t need = n;
+  if (b->n_timers && b->K) {
+    const uint64_t per_slot = (b->min_period != UINT64_MAX && w > b->last_watermark) ? (w - b->last_watermark) / b->min_period + 2 : 2;
+    need += (uint64_t)b->K * per_slot;
+  }
+  if (b->room_lb >= need) { b->room_lb -= need; b->st.admit_skipped++; return CPBUS_OK; }   // provably fits: no kernel, no sync
+  CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, 3 * sizeof(unsigned long long), b->stream));   // overflow, overwritten, max_used
   const uint32_t threads = 256, grid = (b->n_next + threads - 1) / threads;
   admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_ctl, b->d_timers, b->n_next, b->R, b->K,
                                                 b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats,
                                                 b->n_paired > 0 ? b->d_pairs : nullptr);
   CK(cudaGetLastError());
-  b->st.kernel_launches++;
-  CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, sizeof(unsigned long long),
+  b->st.kernel_launches++; b->st.admit_passes++;
+  CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, 3 * sizeof(unsigned long long),
                      cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *ok = b->h_stats->admit_overflow == 0;
+  const uint64_t used = b->h_stats->admit_max_used;            // fullest mailbox, this batch included
+  // admitted: the batch is in; refused: nothing was appended, so the fullest mailbox holds at most `used` minus its share (>= 0):
+  // keep the conservative figure either way
+  b->room_lb = used >= b->R ? 0 : b->R - used;
   return CPBUS_OK;
 }
 
@@ -490,6 +505,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->cfg = *cfg; b->cfg.ring_cap = R; b->cfg.batch_cap = B;
   b->N = cfg->n_max_subs; b->R = R; b->B = B; b->K = K;
   b->lossless = cfg->flags & CPBUS_CFG_LOSSLESS; b->use_digest = cfg->flags & CPBUS_CFG_DIGEST;
+  b->room_lb = R;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
   if (const char* e = getenv("CPBUS_H2D_SPIN_US")) b->h2d_spin_us = atoi(e);
   if (const char* e = getenv("CPBUS_ORDER")) b->use_order = atoi(e) != 0;
@@ -1315,6 +1331,21 @@ int cpbus_drain_many(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_event* ou
   if (hi) CK(cudaMemcpyAsync(out, b->d_drain, hi * sizeof(cpbus_event), cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *total = tot;
+  return CPBUS_OK;
+}
+
+// Device-side consumer: every mailbox of this shard is read to the end and its records are discarded.
+int cpbus_consume_all(cpbus_t* b) {
+  if (!b) return CPBUS_EINVAL;
+  std::lock_guard<std::mutex> g(b->mu);
+  int rc = dev_guard(b); if (rc) return rc;
+  if (b->n_next) {
+    const uint32_t threads = 256, grid = std::min<uint32_t>((b->n_next + threads - 1) / threads, (uint32_t)b->sm_count * 8);
+    consume_all_kernel<<<grid, threads, 0, b->stream>>>(b->d_ctl, b->n_next);
+    CK(cudaGetLastError());
+    b->st.kernel_launches++;
+  }
+  b->room_lb = b->R;   // stream-ordered behind every earlier fan-out: from here on every mailbox is empty
   return CPBUS_OK;
 }
 

@@ -27,6 +27,25 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef CPBUS_CTAS_PER_SM
 #define CPBUS_CTAS_PER_SM 4
 #endif
+// A/B build switches (scripts/gpu_ab.sh builds variants with -D...=0/1 and times them on one box; defaults = best measured)
+#ifndef CPBUS_SWIZZLE
+#define CPBUS_SWIZZLE 1      // conflict-free shared-memory record reads (lanes 4-7 of each quarter warp fetch their halves in swapped order)
+#endif
+#ifndef CPBUS_TICKS_REG
+#define CPBUS_TICKS_REG 1    // dense+ticks copy loop: tick positions in registers (ballots) instead of shared-memory loads
+#endif
+#ifndef CPBUS_COLD_EARLY
+#define CPBUS_COLD_EARLY 1   // cold half of the timer slot loaded before the copy loop instead of after it
+#endif
+#ifndef CPBUS_UNROLL2
+#define CPBUS_UNROLL2 1      // dense+ticks copy loop: two chunks per iteration
+#endif
+#ifndef CPBUS_EARLY_PF
+#define CPBUS_EARLY_PF 1     // prefetch.L2 of the warp's first control block / timer slot at kernel entry
+#endif
+#ifndef CPBUS_ORD_PF
+#define CPBUS_ORD_PF 1       // ORDERED build: prefetch.L2 of the whole block's control blocks once the ids are known
+#endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
 constexpr uint32_t kPairBit = 0x10000000u;     // mask word bit 28: subscriber has a {code, source} pair table
@@ -62,7 +81,9 @@ constexpr int kStatSlots = 256;
 struct __align__(32) DevStatSlot { unsigned long long deliveries, ticks, pad[2]; };
 struct DevStats {
   DevStatSlot slot[kStatSlots];
-  unsigned long long admit_overflow, overwritten, pad[2];
+  unsigned long long admit_overflow, overwritten;
+  unsigned long long admit_max_used;   // lossless admission: max over mailboxes of (undrained records + what the batch would append)
+  unsigned long long pad;
 };
 
 // Accounting of batches that reach the bus already in device memory (cpbus_publish_device*, cpbus_stream_fanout).  What
@@ -247,6 +268,10 @@ __device__ __forceinline__ void st_half(void* dst, const uint4& a, bool hinted) 
 // Lanes 4-7 of each quarter therefore fetch their two halves in the opposite order: each wavefront then covers all 32
 // banks, and two selects per register put the halves back in place.  No re-layout of the TMA-staged batch is needed.
 __device__ __forceinline__ void lds_record(const uint4* s4, uint32_t i, uint32_t sw, uint4& a, uint4& b) {
+#if !CPBUS_SWIZZLE
+  a = s4[2 * i]; b = s4[2 * i + 1]; (void)sw;
+  return;
+#endif
   const uint4 x = s4[2 * i + sw], y = s4[2 * i + (sw ^ 1u)];
   a.x = sw ? y.x : x.x; a.y = sw ? y.y : x.y; a.z = sw ? y.z : x.z; a.w = sw ? y.w : x.w;
   b.x = sw ? x.x : y.x; b.y = sw ? x.y : y.y; b.z = sw ? x.z : y.z; b.w = sw ? x.w : y.w;
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   uint32_t pos = ORDERED ? (blockIdx.x * kWarpsPerCta + warp) * p.spw : blockIdx.x * kWarpsPerCta + warp;
   uint32_t my_ids = 0;
   if (ORDERED && pos + lane < min(pos + p.spw, p.n_order)) my_ids = __ldg(p.order + pos + lane);   // static data: safe before the wait
-  if (!ORDERED && pos < p.n_subs && lane == 0) {
+  if (CPBUS_EARLY_PF && !ORDERED && pos < p.n_subs && lane == 0) {
     // the first control block (and timer slot) of this warp: pull it towards L2 now, so that the load after the prologue
     // does not pay a DRAM round trip behind the write stream.  L2 is the point of coherence: a prefetch can never make
     // the later load see stale data, so this is safe before griddepcontrol.wait.
@@ -374,6 +399,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
 
   const bool keep = p.hints & 1u;
   // (the evict_last policy is materialised at each use — one instruction — rather than held in two registers)
+  if (CPBUS_ORD_PF && ORDERED && pos + lane < min(pos + p.spw, p.n_order))   // mask order scatters the ids: lane l prefetches ITS mailbox's control block
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ctl + my_ids));
 
   // ---- per-batch descriptor: computed ONCE per launch by CTA 0, copied by everyone else ----
   // descriptor = [rhash | meta | Q | summary {present, has_unicast, hist[32]}]: 24*cap + 16 + 160 bytes, the same layout in
@@ -664,15 +691,21 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       if (DIGEST) dsum = s_q[n];
     } else if (dense) {
       // ================= dense run with interleaved ticks: O(#ticks) bookkeeping =================
+      if (CPBUS_COLD_EARLY && TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: needed only for the tick records after the
+        uint4 cold;                        // copy loop, but issued HERE so that its DRAM round trip hides under the copy (round 2 ncu:
+        ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, keep);   // 13 % of stalls sat on it)
+        tk_src = cold.x; tk_fired = cold.y;
+      }
       if (tk_valid) my_tick[tk_rank] = tk_pos;
       __syncwarp();
       k = n + n_ticks;
       // event i lands at i + #{ticks with pos <= i}.  Lane r keeps the r-th smallest tick position in a register, so per
       // 32-event chunk the count is two ballots and a bit mask — no shared-memory round trip in the copy loop (round 1:
       // 34 % of this path's stall samples sat on the my_tick[] loads feeding these compares).
+#if CPBUS_TICKS_REG
       const uint32_t T = (uint32_t)lane < n_ticks ? my_tick[lane] : 0xFFFFFFFFu;
-#pragma unroll 1
-      for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+      // destination of event i = c0 + lane of the chunk starting at c0
+      auto slot_of = [&](uint32_t c0) -> uint32_t {
         const uint32_t before = __popc(__ballot_sync(0xffffffffu, T <= c0));          // ticks at or in front of the chunk's first event
         const bool in = T > c0 && T < c0 + 32u;                                        // ... strictly inside the chunk
         const uint32_t n_in = __popc(__ballot_sync(0xffffffffu, in));
@@ -684,13 +717,46 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           else                                                                         // several ticks share a position: count them one by one
             for (uint32_t t = before; t < n_ticks && my_tick[t] < c0 + 32u; t++) out += (my_tick[t] <= i) ? 1u : 0u;
         }
+        return out;
+      };
+      uint32_t c0 = 0;
+#if CPBUS_UNROLL2
+#pragma unroll 1
+      for (; c0 + 64 <= n; c0 += 64) {   // two chunks per iteration: both records' shared-memory loads are in flight before the selects
+        const uint32_t o0 = slot_of(c0), o1 = slot_of(c0 + 32);
+        uint4 a0, b0, a1, b1;
+        lds_record(s4, c0 + lane, sw, a0, b0);
+        lds_record(s4, c0 + 32 + lane, sw, a1, b1);
+        st_record<STORE>(ring + (((uint32_t)tail + o0) & Rm), a0, b0);
+        st_record<STORE>(ring + (((uint32_t)tail + o1) & Rm), a1, b1);
+      }
+#endif
+#pragma unroll 1
+      for (; c0 < n; c0 += 32) {
+        const uint32_t out = slot_of(c0);
+        if (c0 + lane < n) {
+          uint4 a, b;
+          lds_record(s4, c0 + lane, sw, a, b);
+          st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
+        }
+      }
+#else
+      // Tick positions are sorted, so the count is warp-uniform for a whole 32-event chunk unless a tick falls strictly inside it
+      uint32_t t_idx = 0;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+        while (t_idx < n_ticks && my_tick[t_idx] <= c0) t_idx++;
+        const uint32_t i = c0 + lane;
+        uint32_t out = i + t_idx;
+        for (uint32_t t = t_idx; t < n_ticks && my_tick[t] < c0 + 32; t++) out += (my_tick[t] <= i) ? 1u : 0u;
         if (i < n) {
           uint4 a, b;
           lds_record(s4, i, sw, a, b);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
         }
       }
-      if (TIMERS && tk_slot < nslots) {   // cold half of the timer slot {source_id, fired}: loaded late, only when something fires
+#endif
+      if (!CPBUS_COLD_EARLY && TIMERS && tk_slot < nslots) {
         uint4 cold;
         ld_half(reinterpret_cast<const unsigned char*>(p.timers + (size_t)s * K + tk_slot) + 16, cold, keep);
         tk_src = cold.x; tk_fired = cold.y;
@@ -996,8 +1062,9 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
                              uint32_t timers_on, DevStats* stats, const uint2* pairs) {
   __shared__ uint32_t hist[32];
   __shared__ uint32_t s_uni;
+  __shared__ unsigned long long s_max;
   if (threadIdx.x < 32) hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_uni = 0;
+  if (threadIdx.x == 0) { s_uni = 0; s_max = 0; }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n_ev; i += blockDim.x) {
     const uint32_t code = batch[i].code, target = batch[i].target;
@@ -1006,36 +1073,49 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
   }
   __syncthreads();
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_subs) return;
-  const SubCtl c = ctl[s];
+  SubCtl c{};
+  if (s < n_subs) c = ctl[s];
   const uint32_t m = c.mask;
-  if (!(m & kActiveBit)) return;
-  uint64_t k = 0;
-  for (uint32_t c = 0; c < CPBUS_N_CODES; c++) if ((m >> c) & 1u) k += hist[c];
-  if (pairs && (m & kPairBit)) {   // second-level filter: broadcast events outside the mask that equal an exact {code, source} case
-    const uint2* my = pairs + (size_t)s * CPBUS_MAX_PAIRS;
-    for (uint32_t i = 0; i < n_ev; i++) {
-      const uint32_t code = batch[i].code;
-      if (batch[i].target != CPBUS_TARGET_ALL || code >= CPBUS_N_CODES || ((m >> code) & 1u)) continue;
-      const uint32_t src = batch[i].source_id;
-      for (uint32_t j = 0; j < CPBUS_MAX_PAIRS; j++) {
-        const uint2 pr = my[j];
-        if (pr.x == kPairNone) break;
-        if (pr.x == code && pr.y == src) { k++; break; }
+  if (s < n_subs && (m & kActiveBit)) {
+    uint64_t k = 0;
+    for (uint32_t cc = 0; cc < CPBUS_N_CODES; cc++) if ((m >> cc) & 1u) k += hist[cc];
+    if (pairs && (m & kPairBit)) {   // second-level filter: broadcast events outside the mask that equal an exact {code, source} case
+      const uint2* my = pairs + (size_t)s * CPBUS_MAX_PAIRS;
+      for (uint32_t i = 0; i < n_ev; i++) {
+        const uint32_t code = batch[i].code;
+        if (batch[i].target != CPBUS_TARGET_ALL || code >= CPBUS_N_CODES || ((m >> code) & 1u)) continue;
+        const uint32_t src = batch[i].source_id;
+        for (uint32_t j = 0; j < CPBUS_MAX_PAIRS; j++) {
+          const uint2 pr = my[j];
+          if (pr.x == kPairNone) break;
+          if (pr.x == code && pr.y == src) { k++; break; }
+        }
       }
     }
+    if (s_uni) {
+      const uint32_t gid = sub_base + s;
+      for (uint32_t i = 0; i < n_ev; i++) if (batch[i].target == gid) k++;
+    }
+    const uint32_t nslots = timers_on ? min((m >> kTimerHintShift) & 0xFu, K) : 0u;
+    for (uint32_t t = 0; t < nslots; t++) {
+      const DevTimer tm = timers[(size_t)s * K + t];
+      if (tm.next_due != kTimerIdle && tm.next_due <= w_now)
+        k += tm.period ? (w_now - tm.next_due) / tm.period + 1u : 1u;
+    }
+    const unsigned long long used = c.tail - c.head + k;
+    if (used > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
+    atomicMax(&s_max, used);
   }
-  if (s_uni) {
-    const uint32_t gid = sub_base + s;
-    for (uint32_t i = 0; i < n_ev; i++) if (batch[i].target == gid) k++;
-  }
-  const uint32_t nslots = timers_on ? min((m >> kTimerHintShift) & 0xFu, K) : 0u;
-  for (uint32_t t = 0; t < nslots; t++) {
-    const DevTimer tm = timers[(size_t)s * K + t];
-    if (tm.next_due != kTimerIdle && tm.next_due <= w_now)
-      k += tm.period ? (w_now - tm.next_due) / tm.period + 1u : 1u;
-  }
-  if (c.tail - c.head + k > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
+  // how full the fullest mailbox would be after this batch: lets the host skip the admission pass (and its sync) for the
+  // following batches while they provably fit
+  __syncthreads();
+  if (threadIdx.x == 0 && s_max) atomicMax(&stats->admit_max_used, s_max);
+}
+
+// Device-side consumer: every mailbox is read to the end and its records are discarded (head = tail).  Stands in for
+// consumers that keep up (benchmarks of the lossless mode; subscribers whose events nobody reads).
+__global__ void consume_all_kernel(SubCtl* ctl, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ctl[i].head = ctl[i].tail;
 }
 
 // Throughput mode: records that were overwritten before the consumer took them.  The fan-out kernel never

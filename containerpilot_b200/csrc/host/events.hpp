@@ -273,7 +273,7 @@ class EventBus {   // events/bus.go:12-22
       if (kv.first->Rx && kv.first->Rx->Closed()) throw Panic("send on closed channel");   // bus.go:135-137
     if (String(event.Code) != "Metric") counter_[{String(event.Code), event.Source}]++;     // bus.go:130-132
     cpbus_event ev{};
-    ev.code = (uint32_t)event.Code; ev.source_id = Intern(event.Source);
+    ev.code = (uint32_t)event.Code; ev.source_id = Intern(event);
     for (;;) {
       int rc = cpbus_publish(h_, &ev, 1);
       if (rc == CPBUS_EAGAIN) { DrainAll(/*blocking=*/true); continue; }   // the Go publisher would block in chansend
@@ -297,7 +297,7 @@ class EventBus {   // events/bus.go:12-22
       for (size_t j = 0; j < n; j++) {
         const Event& e = events[i + j];
         if (String(e.Code) != "Metric") counter_[{String(e.Code), e.Source}]++;            // bus.go:130-132
-        evs[j].code = (uint32_t)e.Code; evs[j].source_id = Intern(e.Source);
+        evs[j].code = (uint32_t)e.Code; evs[j].source_id = Intern(e);
       }
       Check(cpbus_publish(h_, evs.data(), n), "cpbus_publish");
       FlushLocked();
@@ -391,6 +391,11 @@ class EventBus {   // events/bus.go:12-22
     if (rc) throw std::runtime_error(std::string(where) + ": " + cpbus_strerror(rc) + " " + cpbus_last_cuda_error());
   }
   uint32_t Intern(const std::string& s) { uint32_t id = 0; Check(cpbus_intern(h_, s.data(), s.size(), &id), "cpbus_intern"); return id; }
+  // A Metric event's Source is a payload ("key|value", control/endpoints.go:125-126), not a name: bounded ephemeral region
+  uint32_t Intern(const Event& e) {
+    if (e.Code != Metric) return Intern(e.Source);
+    uint32_t id = 0; Check(cpbus_intern_ephemeral(h_, e.Source.data(), e.Source.size(), &id), "cpbus_intern_ephemeral"); return id;
+  }
   std::string Source(uint32_t id) {
     size_t n = 0; cpbus_source(h_, id, nullptr, 0, &n);
     std::string s(n, '\0'); if (n) cpbus_source(h_, id, &s[0], n, &n);
@@ -495,7 +500,7 @@ inline void Subscriber::Receive(const Event& e) {                               
   if (Bus && id_ != UINT32_MAX) {   // direct mailbox write, ordered with publishes, bypasses the filter
     std::lock_guard<std::recursive_mutex> l(Bus->lock_);
     cpbus_event ev{};
-    ev.code = (uint32_t)e.Code; ev.source_id = Bus->Intern(e.Source);
+    ev.code = (uint32_t)e.Code; ev.source_id = Bus->Intern(e);
     for (;;) {
       int rc = cpbus_send(Bus->h_, id_, &ev);
       if (rc == CPBUS_EAGAIN) { Bus->DrainAll(true); continue; }

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -202,6 +203,7 @@ class Parser {
     p_++;
     SkipWs();
     if (p_ < end_ && *p_ == '}') { p_++; return true; }
+    std::unordered_map<std::string, size_t> index;   // duplicate keys: the last value wins, the first position stays (O(1) per key)
     for (;;) {
       SkipWs();
       if (p_ >= end_ || *p_ != '"') return false;
@@ -213,9 +215,9 @@ class Parser {
       SkipWs();
       Json val;
       if (!ParseValue(&val, depth + 1)) return false;
-      bool replaced = false;
-      for (auto& kv : out->obj) if (kv.first == key) { kv.second = std::move(val); replaced = true; break; }
-      if (!replaced) out->obj.emplace_back(std::move(key), std::move(val));
+      auto found = index.find(key);
+      if (found != index.end()) out->obj[found->second].second = std::move(val);
+      else { index.emplace(key, out->obj.size()); out->obj.emplace_back(std::move(key), std::move(val)); }
       SkipWs();
       if (p_ >= end_) return false;
       if (*p_ == ',') { p_++; continue; }

@@ -178,7 +178,7 @@ class EventBus:
         for sub in self._subs:
             if sub.Rx is not None and sub.Rx.closed:
                 raise BusPanic("send on closed channel")     # bus.go:135-137
-        rc = self._bus.publish(event.Code, self._bus.intern(event.Source))
+        rc = self._bus.publish(event.Code, self._intern(event))
         if rc == nat.EAGAIN:
             raise BlockingIOError("Publish would block: a subscriber mailbox is full")
         nat.check(rc, "cpbus_publish")
@@ -191,11 +191,16 @@ class EventBus:
                 raise BusPanic("send on closed channel")     # bus.go:135-137
         batch = np.zeros(len(events), dtype=EVENT_DTYPE)
         batch["code"] = [e.Code for e in events]
-        batch["source_id"] = [self._bus.intern(e.Source) for e in events]
+        batch["source_id"] = [self._intern(e) for e in events]
         rc = self._bus.publish_many(batch)
         if rc == nat.EAGAIN:
             raise BlockingIOError("Publish would block: a subscriber mailbox is full")
         nat.check(rc, "cpbus_publish")
+
+    def _intern(self, event: Event) -> int:
+        """Source -> id.  A Metric event's Source is a payload ("key|value", control/endpoints.go:125-126), not a name:
+        it goes to the bounded ephemeral region so the intern table cannot grow with every posted value."""
+        return self._bus.intern_ephemeral(event.Source) if event.Code == Metric else self._bus.intern(event.Source)
 
     def PublishSignal(self, sig: str):      # bus.go:144-146
         self.Publish(Event(Signal, sig))
@@ -218,7 +223,7 @@ class EventBus:
 
     # ---- used by Chan / Subscriber ----
     def _send(self, sub, event: Event):
-        rc = self._bus.send(sub._id, event.Code, self._bus.intern(event.Source))
+        rc = self._bus.send(sub._id, event.Code, self._intern(event))
         if rc == nat.EAGAIN:
             raise BlockingIOError("send would block: mailbox full")
         nat.check(rc, "cpbus_send")

@@ -92,11 +92,14 @@ def metric_events(body) -> list | None:
     """The events PostMetric would publish for this request body, in document order; None = the body does not decode
     into a map[string]interface{} (the handler answers 422)."""
     if isinstance(body, (bytes, bytearray)):
-        # encoding/json replaces invalid UTF-8 inside strings with U+FFFD; outside strings the replacement character is a
-        # syntax error, as the raw bytes are for Go
-        body = bytes(body).decode("utf-8", errors="replace")
+        # encoding/json replaces EVERY invalid byte inside a string with its own U+FFFD (utf8.DecodeRune returns RuneError
+        # with width 1), where Python's errors="replace" folds a truncated multi-byte sequence into a single one:
+        # b'\xe2\x82A' is two U+FFFD + 'A' in Go.  surrogateescape keeps one (lone) surrogate per bad byte, and
+        # _valid_utf8 below turns each into U+FFFD; outside strings they are a syntax error, as the raw bytes are for Go.
+        body = bytes(body).decode("utf-8", errors="surrogateescape")
     try:
-        doc = json.loads(body, parse_constant=_reject_constant)
+        # parse_int=float: every JSON number decodes to float64 in Go, so `-0` stays negative zero and prints "-0"
+        doc = json.loads(body, parse_constant=_reject_constant, parse_int=float)
     except (ValueError, RecursionError):
         return None
     if doc is None:                                          # `null` unmarshals into a nil map without error: nothing to publish

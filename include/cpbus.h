@@ -77,6 +77,11 @@ enum {
 /* cpbus_config.flags */
 #define CPBUS_CFG_LOSSLESS 0x1u /* reference semantics: never drop; a full mailbox
                                    stalls the publisher (events/subscriber.go:30-32).
+                                   The library keeps a lower bound of the free room of
+                                   the fullest mailbox: while a batch provably fits it
+                                   goes straight to the fan-out; the admission kernel
+                                   (and its host sync) runs only when the bound is used
+                                   up, and refreshes it exactly.
                                    Without it the bus runs in overwrite-oldest
                                    throughput mode (no consumer needed).          */
 #define CPBUS_CFG_DIGEST   0x2u /* maintain the per-subscriber order-sensitive
@@ -128,6 +133,8 @@ typedef struct cpbus_stats_t {
   uint64_t intern_bytes;   /* ... and their total length                          */
   uint64_t ephemeral_live; /* payload strings currently held by the bounded ephemeral region (cpbus_intern_ephemeral) */
   uint64_t ephemeral_recycled; /* ephemeral ids that have been recycled so far   */
+  uint64_t admit_passes;   /* lossless mode: flushes that needed the admission kernel (+ one host sync) ... */
+  uint64_t admit_skipped;  /* ... and flushes that provably fitted and went straight to the fan-out        */
 } cpbus_stats_t;
 
 typedef struct cpbus cpbus_t;
@@ -269,6 +276,10 @@ int cpbus_drain(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, siz
  * *total = records returned.  This is what the `chan Event` pump of a shim with many subscribers calls. */
 int cpbus_drain_many(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_event* out, size_t cap,
                      uint32_t* offsets, uint32_t* counts, size_t* total);
+/* Device-side consumer: every mailbox is read to the end and its records are discarded (head = tail), ordered behind
+ * every earlier fan-out on the bus stream.  For subscribers nobody reads, and for measuring the lossless mode with
+ * consumers that keep up. */
+int cpbus_consume_all(cpbus_t* bus);
 /* Last min(cap, ring_cap, count) delivered records, oldest first, without consuming. */
 int cpbus_peek_window(cpbus_t* bus, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n);
 int cpbus_digest(cpbus_t* bus, uint32_t first_sub, uint32_t n, cpbus_digest_t* out);

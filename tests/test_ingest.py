@@ -140,3 +140,30 @@ def test_cpp_and_python_mirrors_agree_on_random_documents():
         assert line == want, body
         n_events += len(evs or [])
     assert n_events > 1000
+
+
+def test_mirrors_agree_on_malformed_bytes_and_negative_zero():
+    """Edge inputs where a careless restatement drifts from encoding/json: every invalid byte inside a string becomes its
+    OWN U+FFFD (Go's utf8.DecodeRune returns width 1), and `-0` is float64 negative zero, printed "-0" by %v."""
+    bodies = [b'{"k":"\xe2\x82A"}', b'{"k":"\xed\xa0\x80"}', b'{"k":"\xf0\x9f\x98"}', b'{"k\xc0\xaf":"\xff\xfe\xfd"}',
+              b'{"a": -0}', b'{"a": -0, "b": [-0, -0.0, 0]}', b'{"a": -0e5}', b'{"a": 100000, "b": 1000000, "c": -1000000}']
+    want_first = ["k|��A", "k|���", "k|���", "k��|���", "a|-0"]
+    for body, want in zip(bodies, want_first):
+        assert ingest.metric_events(body)[0].Source == want, body
+    out = subprocess.run([_cpp_binary(), "--events"], input=b"\n".join(bodies) + b"\n", capture_output=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.decode("utf-8").split("\n")[:-1]
+    assert len(lines) == len(bodies)
+    for body, line in zip(bodies, lines):
+        evs = ingest.metric_events(body)
+        assert line == "\t".join(["200"] + [e.Source for e in evs]), body
+
+
+def test_cpp_decoder_handles_a_body_with_1e5_keys_in_linear_time():
+    body = ("{" + ",".join(f'"k{i}": {i}' for i in range(100_000)) + ',"k7": "again"}').encode()
+    import time
+    t0 = time.perf_counter()
+    out = subprocess.run([_cpp_binary(), "--events"], input=body + b"\n", capture_output=True, timeout=60)
+    assert out.returncode == 0 and time.perf_counter() - t0 < 10
+    fields = out.stdout.decode().rstrip("\n").split("\t")
+    assert fields[0] == "200" and len(fields) == 100_001 and fields[8] == "k7|again"     # last value wins, first position stays
