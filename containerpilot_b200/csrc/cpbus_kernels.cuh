@@ -29,22 +29,26 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #endif
 // A/B build switches (scripts/gpu_ab.sh builds variants with -D...=0/1 and times them on one box; defaults = best measured)
 #ifndef CPBUS_SWIZZLE
-#define CPBUS_SWIZZLE 1      // conflict-free shared-memory record reads (lanes 4-7 of each quarter warp fetch their halves in swapped order)
+#define CPBUS_SWIZZLE 2      // shared-memory record reads with lanes 4-7 of each quarter warp fetching their halves in swapped order:
+                             // 0 = never, 1 = every path, 2 = only the gathered reads of the filtered path in the ORDERED build.
+                             // Measured (profiles/r02_ab_kernel_variants.md): the swizzle removes the bank conflicts everywhere, but on
+                             // the dense paths the two extra live registers per record cost more than the conflicts did
+                             // (config 2: 154 -> 166 us per launch, config 3: 2741 -> 2836); on the gathered reads it gains 1 %.
 #endif
 #ifndef CPBUS_TICKS_REG
 #define CPBUS_TICKS_REG 1    // dense+ticks copy loop: tick positions in registers (ballots) instead of shared-memory loads
 #endif
 #ifndef CPBUS_COLD_EARLY
-#define CPBUS_COLD_EARLY 1   // cold half of the timer slot loaded before the copy loop instead of after it
+#define CPBUS_COLD_EARLY 1   // (+1 % on config 3 once the loop is not unrolled) cold half of the timer slot loaded before the copy loop instead of after it
 #endif
 #ifndef CPBUS_UNROLL2
-#define CPBUS_UNROLL2 1      // dense+ticks copy loop: two chunks per iteration
+#define CPBUS_UNROLL2 0      // dense+ticks copy loop: two chunks per iteration (measured: no gain, costs registers)
 #endif
 #ifndef CPBUS_EARLY_PF
-#define CPBUS_EARLY_PF 1     // prefetch.L2 of the warp's first control block / timer slot at kernel entry
+#define CPBUS_EARLY_PF 0     // (measured: neutral) prefetch.L2 of the warp's first control block / timer slot at kernel entry
 #endif
 #ifndef CPBUS_ORD_PF
-#define CPBUS_ORD_PF 1       // ORDERED build: prefetch.L2 of the whole block's control blocks once the ids are known
+#define CPBUS_ORD_PF 0       // (measured: -1.3 % on config 5) ORDERED build: prefetch.L2 of the whole block's control blocks once the ids are known
 #endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
@@ -267,11 +271,12 @@ __device__ __forceinline__ void st_half(void* dst, const uint4& a, bool hinted) 
 // (round 1 ncu: l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld = 0.74 per record, 44 % of stall samples short_sb).
 // Lanes 4-7 of each quarter therefore fetch their two halves in the opposite order: each wavefront then covers all 32
 // banks, and two selects per register put the halves back in place.  No re-layout of the TMA-staged batch is needed.
+template <bool GATHER = false>
 __device__ __forceinline__ void lds_record(const uint4* s4, uint32_t i, uint32_t sw, uint4& a, uint4& b) {
-#if !CPBUS_SWIZZLE
-  a = s4[2 * i]; b = s4[2 * i + 1]; (void)sw;
-  return;
-#endif
+  if (CPBUS_SWIZZLE == 0 || (CPBUS_SWIZZLE == 2 && !GATHER)) {
+    a = s4[2 * i]; b = s4[2 * i + 1];
+    return;
+  }
   const uint4 x = s4[2 * i + sw], y = s4[2 * i + (sw ^ 1u)];
   a.x = sw ? y.x : x.x; a.y = sw ? y.y : x.y; a.z = sw ? y.z : x.z; a.w = sw ? y.w : x.w;
   b.x = sw ? x.x : y.x; b.y = sw ? x.y : y.y; b.z = sw ? x.z : y.z; b.w = sw ? x.w : y.w;
@@ -818,8 +823,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (; o + 32 < k; o += 64) {   // two outputs per lane per iteration: their index/record/hash loads are independent
           const uint32_t i0 = my_idx[o], i1 = my_idx[o + 32];
           uint4 a0, b0, a1, b1;
-          lds_record(s4, i0, sw, a0, b0);
-          lds_record(s4, i1, sw, a1, b1);
+          lds_record<ORDERED>(s4, i0, sw, a0, b0);
+          lds_record<ORDERED>(s4, i1, sw, a1, b1);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
           st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
           if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
@@ -827,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (; o < k; o += 32) {
           const uint32_t i = my_idx[o];
           uint4 a, b;
-          lds_record(s4, i, sw, a, b);
+          lds_record<ORDERED>(s4, i, sw, a, b);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
           if (hashing) acc = acc * p32 + s_rhash[i];
         }

@@ -28,6 +28,7 @@ def run(lib_path, name, n_subs, timers, zipf, steps=60, warm=30, B=512):
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     cfg = Config(); cfg.n_max_subs, cfg.ring_cap, cfg.batch_cap, cfg.timers_per_sub, cfg.flags, cfg.device = n_subs, 1024, B, timers, 2, 0
     cfg.stream = C.c_void_p(stream.cuda_stream)
+    cfg.store_path = int(os.environ.get('AB_STORE', '0'))
     h = C.c_void_p()
     assert lib.cpbus_create(C.byref(cfg), C.byref(h)) == 0
     masks = tr.zipf_masks(n_subs, zipf, 0xC0DEB205) if zipf else np.full(n_subs, 0x1FFFF, dtype=np.uint32)
@@ -59,8 +60,12 @@ def run(lib_path, name, n_subs, timers, zipf, steps=60, warm=30, B=512):
 
 
 if __name__ == "__main__":
-    for rep in range(2):
+    for rep in range(int(os.environ.get("AB_REPS", "2"))):
+        which = os.environ.get("AB_CONFIGS", "config2,config3,config5").split(",")
         for lib in sys.argv[1:]:
-            run(os.path.abspath(lib), "config2", 65_536, 0, None, steps=200, warm=100)
-            run(os.path.abspath(lib), "config3", 1_048_576, 1, None)
-            run(os.path.abspath(lib), "config5", 1_048_576, 0, 1.0)
+            if "config2" in which:
+                run(os.path.abspath(lib), "config2", 65_536, 0, None, steps=200, warm=100)
+            if "config3" in which:
+                run(os.path.abspath(lib), "config3", 1_048_576, 1, None)
+            if "config5" in which:
+                run(os.path.abspath(lib), "config5", 1_048_576, 0, 1.0)
