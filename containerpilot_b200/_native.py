@@ -20,7 +20,7 @@ CFG_LOSSLESS, CFG_DIGEST = 0x1, 0x2
 STORE_AUTO, STORE_V4, STORE_V8, STORE_BULK = 0, 1, 2, 3
 
 OK, EINVAL, ENOMEM, ECUDA, EAGAIN, ENOSPC, ENOENT, ECLOSED, ENODEV, EORDER, ETIMEDOUT = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
-PUT_STAMP, PUT_RAW = 0, 1
+PUT_STAMP, PUT_RAW, PUT_NOWAIT = 0, 1, 2
 EPHEMERAL_BIT, EPHEMERAL_SLOTS = 0x80000000, 65536
 
 

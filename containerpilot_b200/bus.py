@@ -177,9 +177,10 @@ class Bus:
         nat.check(self._lib.cpbus_stream_attach(self._h, owner_stream, consumer_index, C.byref(st)), "cpbus_stream_attach")
         return st
 
-    def stream_put(self, st, events: np.ndarray, now_ns: int, raw: bool = False) -> int:
+    def stream_put(self, st, events: np.ndarray, now_ns: int, raw: bool = False, nowait: bool = False) -> int:
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
-        return self._lib.cpbus_stream_put(st, ev.ctypes.data if ev.size else None, ev.size, now_ns, nat.PUT_RAW if raw else nat.PUT_STAMP)
+        flags = (nat.PUT_RAW if raw else nat.PUT_STAMP) | (nat.PUT_NOWAIT if nowait else 0)
+        return self._lib.cpbus_stream_put(st, ev.ctypes.data if ev.size else None, ev.size, now_ns, flags)
 
     def stream_fanout(self, st, n: int, now_ns: int) -> int:
         return self._lib.cpbus_stream_fanout(st, n, now_ns)

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -262,7 +263,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
   if (n == 0 && b->n_timers == 0 && !sa) return CPBUS_OK;   // (a stream batch is always consumed: its slot must be acknowledged)
   FanoutParams p{};
   p.batch = d_src; p.ring = b->d_ring; p.ctl = b->d_ctl; p.timers = b->d_timers; p.stats = b->d_stats; p.pow_table = b->d_pow; p.launch_seq = ++b->launch_seq;
-  p.desc = b->d_desc + (p.launch_seq & 1) * fanout_desc_bytes(2048);   // two descriptor buffers: launch i+1 may write while launch i reads
+  p.desc = b->d_desc + (p.launch_seq & 1) * ((fanout_desc_bytes(2048) + 255) & ~(size_t)255);   // two descriptor buffers: launch i+1 may write while launch i reads
   p.desc_ready = b->d_desc_ready + (p.launch_seq & 1) * 16; p.w_now = w;
   p.result = b->d_result + (size_t)(p.launch_seq % kResultRing) * kResultSub;
   p.result_next = b->d_result + (size_t)((p.launch_seq + 1) % kResultRing) * kResultSub;
@@ -536,7 +537,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   ALLOC(b->d_ctl, N * sizeof(SubCtl)); ALLOC(b->d_order, N * 4);
   if (K) ALLOC(b->d_timers, N * K * sizeof(DevTimer));
   ALLOC(b->d_stats, sizeof(DevStats)); ALLOC(b->d_fold, 32 * cpbus::kFoldSlots); ALLOC(b->d_pow, kPowTableLen * 8);
-  ALLOC(b->d_desc, 2 * fanout_desc_bytes(2048)); ALLOC(b->d_desc_ready, 256);
+  ALLOC(b->d_desc, 2 * ((fanout_desc_bytes(2048) + 255) & ~(size_t)255)); ALLOC(b->d_desc_ready, 256);
   if (cudaMemsetAsync(b->d_desc_ready, 0, 256, b->stream) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
   if (cudaStreamCreateWithFlags(&b->result_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CPBUS_ECUDA);
@@ -1205,13 +1206,21 @@ int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64
   int rc = dev_guard(b); if (rc) return rc;
   const unsigned long long q = st->put_seq + 1;
   if (q > st->n_slots && st->min_ack + st->n_slots < q) {
-    // the slot still holds batch q - n_slots: every consumer must have pulled it (acks are device words: refresh the cache)
-    CK(cudaMemcpyAsync(st->h_ack, st->ack, (size_t)st->n_consumers * 32, cudaMemcpyDeviceToHost, st->put_stream));
-    CK(cudaStreamSynchronize(st->put_stream));
-    unsigned long long m = ~0ull;
-    for (uint32_t c = 0; c < st->n_consumers; c++) m = std::min(m, st->h_ack[4 * c]);
-    st->min_ack = m;
-    if (st->min_ack + st->n_slots < q) return CPBUS_EAGAIN;
+    // The slot still holds batch q - n_slots: every consumer must have pulled it.  Acks are device words written by the
+    // consumers' kernels; refresh the cached minimum, and — unless the caller asked not to wait — give consumers that
+    // are merely behind (their launches are queued, the GPUs are busy) up to the stream timeout to get there.
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto budget = std::chrono::microseconds(b->stream_spin_us ? b->stream_spin_us : 2000000u);
+    for (;;) {
+      CK(cudaMemcpyAsync(st->h_ack, st->ack, (size_t)st->n_consumers * 32, cudaMemcpyDeviceToHost, st->put_stream));
+      CK(cudaStreamSynchronize(st->put_stream));
+      unsigned long long m = ~0ull;
+      for (uint32_t c = 0; c < st->n_consumers; c++) m = std::min(m, st->h_ack[4 * c]);
+      st->min_ack = m;
+      if (st->min_ack + st->n_slots >= q) break;
+      if ((flags & CPBUS_PUT_NOWAIT) || std::chrono::steady_clock::now() - t0 > budget || *(volatile unsigned int*)b->h_err) return CPBUS_EAGAIN;
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
   }
   const int s = (int)(q % cpbus_stream::kStage);
   CK(cudaEventSynchronize(st->staged_done[s]));   // the pinned buffers of batch q - kStage have left the host

@@ -319,6 +319,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
 //   [40cap, 48cap)        {codebit, target} per event
 //   [48cap, 56cap+16)     Q[i] = sum_{j<i} H(e_j) P^(n-1-j): prefix sums for O(#ticks) digests of dense runs
 //   [.., +160)            descriptor summary {present, has_unicast, hist[32]} (lands with the descriptor's bulk copy)
+//   [.., +4096)           PAIRS build only: presence filter of the batch's {code, source} keys (same bulk copy)
 //   then                  powers P^0 .. P^(cap+64), BatchSummary (mbarriers, per-CTA accumulators), per-warp tick scratch
 struct BatchSummary {
   uint64_t mbar;
@@ -332,7 +333,7 @@ struct BatchSummary {
   uint64_t red[kWarpsPerCta];
 };
 
-__host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 160; }
+__host__ __device__ inline size_t fanout_desc_bytes(uint32_t cap) { return (size_t)24 * cap + 16 + 160 + kPairFilterBytes; }
 
 __host__ __device__ inline size_t fanout_smem_bytes(uint32_t cap) {
   const size_t scratch = (cap / 2u > 32u ? cap / 2u : 32u) * sizeof(uint32_t);
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   uint2* s_meta = reinterpret_cast<uint2*>(smem + (size_t)cap * 40);
   uint64_t* s_q = reinterpret_cast<uint64_t*>(smem + (size_t)cap * 48);
   uint32_t* s_dsum = reinterpret_cast<uint32_t*>(s_q + cap + 2);        // descriptor summary: present, has_unicast, hist[32], pad (160 B)
-  uint64_t* s_pow = s_q + cap + 2 + 20;                              // 16-byte aligned (TMA destination)
+  uint32_t* s_present = s_dsum + 40;                                  // PAIRS build: the batch's {code, source} presence filter (4 KiB), part of the descriptor
+  uint64_t* s_pow = s_q + cap + 2 + 20 + (PAIRS ? kPairFilterWords / 2 : 0);   // 16-byte aligned (TMA destination)
   BatchSummary* s_sum = reinterpret_cast<BatchSummary*>(s_pow + cap + 66);
   uint32_t* s_tick = reinterpret_cast<uint32_t*>(s_sum + 1);
 
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // descriptor = [rhash | meta | Q | summary {present, has_unicast, hist[32]}]: 24*cap + 16 + 160 bytes, the same layout in
   // shared memory and in HBM, so the copy is ONE bulk (TMA) transfer per CTA.  The flag word carries the launch ordinal and,
   // in bit 63, "aborted" (stream batch missing), so a consumer needs no second load to learn it.
-  const uint32_t desc_bytes = 24u * cap + 16u + 160u;
+  const uint32_t desc_bytes = 24u * cap + 16u + 160u + (PAIRS ? kPairFilterBytes : 0u);
   uint4* s_desc = reinterpret_cast<uint4*>(s_rhash);
   uint4* g_desc = reinterpret_cast<uint4*>(p.desc);
   constexpr unsigned long long kAbortBit = 1ull << 63;
@@ -533,6 +535,17 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       if (tid == 0) { uint64_t t = 0; for (int w = 0; w < kWarpsPerCta; w++) t += s_sum->red[w]; s_q[nd] = t; }
       __syncthreads();
     }
+    if (PAIRS) {   // presence filter over the batch's broadcast {code, source} keys: built ONCE per launch, shipped with the descriptor
+      for (uint32_t i = tid; i < kPairFilterWords; i += kThreads) s_present[i] = 0u;
+      __syncthreads();
+      for (uint32_t i = tid; i < nd; i += kThreads) {
+        if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
+        const uint32_t h = pair_key_hash(s_batch[i].code, s_batch[i].source_id);
+        atomicOr(&s_present[(h & 32767u) >> 5], 1u << (h & 31u));
+        atomicOr(&s_present[((h >> 15) & 32767u) >> 5], 1u << ((h >> 15) & 31u));
+      }
+      __syncthreads();
+    }
     if (lead) {
       for (uint32_t i = tid; i < desc_bytes / 16u; i += kThreads) g_desc[i] = s_desc[i];
       __threadfence();
@@ -547,18 +560,6 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     mbar_wait(&s_sum->mbar, (staged && n && !s_sum->abort_launch) ? 1u : 0u);
   }
   const bool aborted = s_sum->abort_launch != 0;   // stream batch missing: this launch delivers nothing and fires no timer
-  if (PAIRS) {   // the presence filter sits behind the per-warp scratch (the host adds kPairFilterBytes)
-    uint32_t* s_present = s_tick + kWarpsPerCta * max(32u, cap / 2u);
-    for (uint32_t i = tid; i < kPairFilterWords; i += kThreads) s_present[i] = 0u;
-    __syncthreads();
-    for (uint32_t i = tid; i < n; i += kThreads) {
-      if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
-      const uint32_t h = pair_key_hash(s_batch[i].code, s_batch[i].source_id);
-      atomicOr(&s_present[(h & 32767u) >> 5], 1u << (h & 31u));
-      atomicOr(&s_present[((h >> 15) & 32767u) >> 5], 1u << ((h >> 15) & 31u));
-    }
-    __syncthreads();
-  }
   const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
   const bool timers_on = TIMERS && p.timers_on && K;
@@ -658,7 +659,6 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       if (lane < CPBUS_MAX_PAIRS) pr = __ldg(p.pairs + (size_t)s * CPBUS_MAX_PAIRS + lane);
       bool hit = false;
       if (pr.x < 32u) {
-        const uint32_t* s_present = s_tick + kWarpsPerCta * scratch_words;
         const uint32_t h = pair_key_hash(pr.x, pr.y);
         hit = ((s_present[(h & 32767u) >> 5] >> (h & 31u)) & (s_present[((h >> 15) & 32767u) >> 5] >> ((h >> 15) & 31u)) & 1u) != 0;
       }

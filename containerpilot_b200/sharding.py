@@ -264,13 +264,15 @@ class LocalShardedBus:
             if count:
                 bus.timer_add_many(first, count, period_ns, source_id0=source_id0 + first)
 
-    def publish(self, events: np.ndarray, now_ns: int, raw: bool = False, lookahead=None):
-        """One batch to every shard: put once, fan out on each GPU."""
+    def publish(self, events: np.ndarray, now_ns: int, raw: bool = False):
+        """One batch to every shard: put once, fan out on each GPU (never ahead of its own fan-outs, so it may wait)."""
         nat.check(self.shards[0][2].stream_put(self._st[0], events, now_ns, raw), "cpbus_stream_put")
         self.fanout(len(events), now_ns)
 
     def put(self, events: np.ndarray, now_ns: int, raw: bool = False) -> int:
-        return self.shards[0][2].stream_put(self._st[0], events, now_ns, raw)
+        """Run ahead of the fan-outs.  One thread drives publisher and consumers here, so this never waits: EAGAIN means
+        "fan out (or sync) first" — the slot's previous batch has not been pulled by every shard yet."""
+        return self.shards[0][2].stream_put(self._st[0], events, now_ns, raw, nowait=True)
 
     def fanout(self, n: int, now_ns: int):
         for g, (_, _, bus) in enumerate(self.shards):

@@ -240,13 +240,18 @@ int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, ui
  *   every step     : [publisher] cpbus_stream_put(st, events, n, now_ns, flags)   (may run ahead by < n_slots batches)
  *                    [all ranks] cpbus_stream_fanout(st, n, now_ns)
  * The consumers must be told n and now_ns of every batch by the caller (SPMD drivers know them; the header carries both
- * and the kernel cross-checks n).  CPBUS_EAGAIN from _put: the slot's previous batch is not yet acknowledged by every
- * consumer — call again after the consumers have advanced.  CPBUS_ETIMEDOUT from _fanout/_status: an earlier stream
+ * and the kernel cross-checks n).  CPBUS_EAGAIN from _put: the slot's previous batch is still not acknowledged by every
+ * consumer after the stream timeout (or at once with CPBUS_PUT_NOWAIT) — call again after the consumers have advanced.  CPBUS_ETIMEDOUT from _fanout/_status: an earlier stream
  * launch gave up waiting for its batch (bounded in-kernel wait, cpbus_stream_set_timeout) and delivered nothing. */
 typedef struct cpbus_stream cpbus_stream_t;
 #define CPBUS_PUT_STAMP 0x0u /* records are stamped like cpbus_publish: seq = running publish ordinal, ts = now_ns,
                                 target = ALL, flags = 0; only code/source_id are read from the caller's records */
 #define CPBUS_PUT_RAW   0x1u /* records are complete (as for cpbus_publish_device): copied verbatim */
+#define CPBUS_PUT_NOWAIT 0x2u /* if the slot's previous batch is not yet acknowledged by every consumer, return
+                                CPBUS_EAGAIN at once.  Default: wait for the consumers (their launches are queued, the
+                                GPUs are busy) up to the stream timeout, then CPBUS_EAGAIN.  A single thread that drives
+                                the publisher AND consumers (LocalShardedBus) must use NOWAIT or never run more than
+                                n_slots batches ahead of its own fan-outs. */
 int cpbus_stream_create(cpbus_t* bus, uint32_t n_slots, uint32_t n_consumers, cpbus_stream_t** out, unsigned char handle[64]);
 int cpbus_stream_open(cpbus_t* bus, const unsigned char handle[64], uint32_t consumer_index, cpbus_stream_t** out);
 /* same-process consumer (one host process driving several GPUs, as the cgo shim does): no IPC handle, the owner's ring is

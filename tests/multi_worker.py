@@ -48,10 +48,8 @@ def main():
             put = 0
             for j in range(nb):
                 while put < nb and put <= j + args.lookahead:
-                    rc = sb.put(recs[put * B:(put + 1) * B], int(wms[put]), raw=True)
-                    if rc == nat.EAGAIN:
-                        break
-                    nat.check(rc, "cpbus_stream_put"); put += 1
+                    # (waits, bounded, for consumers that are merely behind: their launches are queued on busy GPUs)
+                    nat.check(sb.put(recs[put * B:(put + 1) * B], int(wms[put]), raw=True), "cpbus_stream_put"); put += 1
                 nat.check(sb.fanout(B, int(wms[j])), "cpbus_stream_fanout")
         else:
             ptr = sb.attach_trace(nb * B * 32)
