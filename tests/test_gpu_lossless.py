@@ -58,7 +58,7 @@ def test_device_consumer_keeps_lossless_mode_on_the_fast_path():
     N, B = 4096, 256
     rng = np.random.default_rng(9)
     masks = np.where(rng.random(N) < 0.5, nat.MASK_ALL, rng.integers(0, 1 << 17, N)).astype(np.uint32)
-    orc = ob.Oracle(N, keep_window=8)
+    orc = ob.Oracle(N, timers_per_sub=1, keep_window=8)
     for m in masks:
         orc.subscribe(int(m))
     with Bus(N, ring_cap=1024, batch_cap=B, lossless=True, timers_per_sub=1) as bus:
