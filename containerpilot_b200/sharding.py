@@ -82,13 +82,14 @@ class ShardedBus(_ShardOps):
 
     def __init__(self, n_subs_total: int, dist=None, rank: int = 0, world: int = 1, device: int = -1, ring_cap: int = 1024,
                  batch_cap: int = 512, timers_per_sub: int = 0, digest: bool = True, stream_slots: int = 64,
-                 stream=None, store_path: int = nat.STORE_AUTO, grid_ctas: int = 0, subs_per_rank: int | None = None):
+                 stream=None, store_path: int = nat.STORE_AUTO, grid_ctas: int = 0, subs_per_rank: int | None = None,
+                 bus_factory=Bus):
         self.dist, self.rank, self.world = dist, rank, world
         if subs_per_rank is not None:               # weak scaling: fixed shard size
             self.first, self.count = rank * subs_per_rank, subs_per_rank
         else:
             self.first, self.count = shard_range(n_subs_total, world, rank)
-        self.bus = Bus(max(self.count, 1), ring_cap=ring_cap, batch_cap=batch_cap, timers_per_sub=timers_per_sub, digest=digest,
+        self.bus = bus_factory(max(self.count, 1), ring_cap=ring_cap, batch_cap=batch_cap, timers_per_sub=timers_per_sub, digest=digest,
                        device=device, sub_id_base=self.first, store_path=store_path, stream=stream, grid_ctas=grid_ctas)
         self.batch_cap = batch_cap
         self._st = None

@@ -96,3 +96,76 @@ def test_world2_broadcast_stream_gives_shard_invariant_digests(tmp_path):
     single = _run_shard(0, N_TOTAL, masks, codes, srcs)
     assert (sharded == single).all()
     assert single[:, 0].min() > 0
+
+
+# ---- ShardedBus's host logic at world_size 2 on CPU/gloo: the construction handshake (IPC handle from rank 0 to the others,
+#      all-or-nothing fallback), SPMD put/fanout routing and the cross-rank digest fold.  The GPU side is replaced by a
+#      recording stand-in (`bus_factory`); the real thing runs in tests/test_gpu_multi.py on hardware. ----
+class _FakeBus:
+    fail_create = False
+
+    def __init__(self, n, **kw):
+        self.n, self.kw, self.calls = n, kw, []
+
+    def stream_create(self, slots, n_consumers):
+        if _FakeBus.fail_create:
+            from containerpilot_b200 import _native as nat
+            raise nat.CpbusError.__new__(nat.CpbusError)
+        self.calls.append(("create", slots, n_consumers))
+        return "st0", b"H" * 64
+
+    def stream_open(self, handle, idx):
+        self.calls.append(("open", handle, idx))
+        return f"st{idx}"
+
+    def stream_put(self, st, ev, now, raw=False, nowait=False):
+        self.calls.append(("put", st, len(ev), now)); return 0
+
+    def stream_fanout(self, st, n, now):
+        self.calls.append(("fanout", st, n, now)); return 0
+
+    def stream_close(self, st):
+        self.calls.append(("close", st))
+
+    def digest_fold(self, first, count):
+        return (count * 10, (first + 1) * 7, 1 << (first % 60), count)
+
+    def close(self):
+        self.calls.append(("destroy",))
+
+
+def _sb_worker(rank, world, port, out, fail):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _FakeBus.fail_create = fail
+        sb = sharding.ShardedBus(37, dist=dist, rank=rank, world=world, bus_factory=_FakeBus, batch_cap=64, stream_slots=8)
+        ev = np.zeros(5, dtype=ob.EVENT_DTYPE)
+        if sb.stream_ok:
+            assert sb.publish(ev, 1000) == 0
+        fold = sb.digest_fold_all()
+        calls = list(sb.bus.calls)
+        sb.close()
+        torch.save({"first": sb.first, "count": sb.count, "ok": sb.stream_ok, "ingest": sb.ingest, "calls": calls + sb.bus.calls[len(calls):],
+                    "fold": fold}, f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("fail", [False, True])
+def test_sharded_bus_handshake_and_routing_at_world2(tmp_path, fail):
+    out = str(tmp_path / "sb")
+    mp.spawn(_sb_worker, args=(2, _free_port(), out, fail), nprocs=2, join=True)
+    r0, r1 = (torch.load(f"{out}.{r}", weights_only=False) for r in (0, 1))
+    assert (r0["first"], r0["count"], r1["first"], r1["count"]) == (0, 19, 19, 18)          # contiguous shards
+    assert r0["fold"] == r1["fold"] == (370, (7 + 140) & (2**64 - 1), 1 ^ (1 << 19), 37)    # sums / xor over both shards
+    if fail:                                                                                 # rank 0 could not create the ring:
+        assert not r0["ok"] and not r1["ok"] and r1["ingest"] == "local"                     # EVERY rank falls back together
+        assert not any(c[0] == "open" for c in r1["calls"])
+        return
+    assert r0["ok"] and r1["ok"] and "nvlink-stream" in r1["ingest"]
+    assert ("create", 8, 2) in r0["calls"] and ("open", b"H" * 64, 1) in r1["calls"]          # the 64-byte handle travelled
+    assert ("put", "st0", 5, 1000) in r0["calls"] and not any(c[0] == "put" for c in r1["calls"])   # only the publisher puts
+    assert ("fanout", "st0", 5, 1000) in r0["calls"] and ("fanout", "st1", 5, 1000) in r1["calls"]  # everyone fans out
+    assert r1["calls"].index(("close", "st1")) < r1["calls"].index(("destroy",))             # importers unmap before destroy
