@@ -2,7 +2,7 @@
 """Stall samples and shared-memory bank conflicts per CUDA SOURCE LINE of a captured kernel.
 ncu's SASS page has no line column, so the per-instruction rows are aligned (by instruction index) with
 `nvdisasm -g` of the same cubin, which carries `//## File ..., line N` markers (-lineinfo build).
-usage: ncu_lines.py <report.ncu-rep> <libcpbus.so that ran> [top]"""
+usage: ncu_lines.py <report.ncu-rep> <libcpbus.so that ran> [top] [source file as of that build]"""
 import csv, io, re, subprocess, sys, tempfile, os, glob
 
 rep, so = sys.argv[1], sys.argv[2]
@@ -44,7 +44,7 @@ for l in dis:
         lines_of.append(cur)
 n = min(len(lines_of), len(data))
 print(f"kernel {kname[:60]}  sass rows {len(data)}  nvdisasm instructions {len(lines_of)}")
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "containerpilot_b200", "csrc", "cpbus_kernels.cuh")).read().split("\n")
+src = open(sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "containerpilot_b200", "csrc", "cpbus_kernels.cuh")).read().split("\n")
 st = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
 agg = {}
 for i in range(n):
