@@ -126,7 +126,8 @@ struct cpbus {
   uint32_t n_paired = 0;                  // active subscribers with a pair table
   uint32_t* d_order = nullptr;            // active subscribers sorted by code mask (ORDERED fan-out)
   uint32_t n_order = 0, n_filtered = 0;   // n_filtered: active subscribers whose mask is not CPBUS_MASK_ALL
-  bool order_dirty = true, use_order = true;
+  bool order_dirty = true;
+  int use_order = 1;                      // CPBUS_ORDER: 0 never, 1 when some subscriber is filtered (default), 2 also for all-ones masks (experiment)
   std::vector<size_t> oneshot_idx;        // armed one-shot timers (index into h_timers)
   std::vector<HostTimer> h_timers;        // N*K, allocated on first timer
   uint32_t n_next = 0, n_active = 0, n_timers = 0;
@@ -276,10 +277,12 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
   p.n_subs = b->n_next; p.ring_cap = b->R; p.K = b->K; p.sub_base = b->cfg.sub_id_base;
   p.use_digest = b->use_digest; p.lossless = b->lossless; p.timers_on = b->n_timers > 0 && b->K > 0;
   p.smem_cap = (n + 31u) & ~31u;
-  // evict_last on control blocks / timer slots pays while they are a small slice of the 126 MB L2
-  // (65,536 subscribers, 2-4 MiB: +3 %); at 1,048,576 subscribers (64 MiB with timers) it costs 8 %.
+  // evict_last on control blocks / timer slots: they are re-read and re-written by every launch while the ring stream passes
+  // through L2 once.  Round 2, same box (gpurun_out/r2k_ab.txt): with the hint at 1,048,576 subscribers config 5 (32 MiB of
+  // control blocks, scattered by the mask order) 1424 -> 1355 us per launch (-4.9 %), config 3 (64 MiB with timer slots)
+  // 2671 -> 2662 (-0.4 %); round 1's kernel had lost 8 % there.  Kept while the hot state is at most half of the 126 MB L2.
   const size_t hot_bytes = (size_t)b->n_next * (sizeof(SubCtl) + (p.timers_on ? b->K * sizeof(DevTimer) : 0));
-  p.hints = b->hints >= 0 ? (uint32_t)b->hints : (hot_bytes <= (16u << 20) ? 1u : 0u);
+  p.hints = b->hints >= 0 ? (uint32_t)b->hints : (hot_bytes <= (64u << 20) ? 1u : 0u);
   const uint32_t need = (b->n_next + kWarpsPerCta - 1) / kWarpsPerCta;
   uint32_t grid = b->cfg.grid_ctas ? std::max(1u, std::min(b->cfg.grid_ctas, need)) : 0u;   // 0: sized from occupancy
   int rc;
@@ -290,7 +293,7 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
   const bool pairs_on = b->n_paired > 0 && b->d_pairs;
   p.pairs = pairs_on ? b->d_pairs : nullptr;
   const size_t smem = fanout_smem_bytes(p.smem_cap) + (pairs_on ? kPairFilterBytes : 0);   // + the batch's {code, source} presence filter
-  if (!pairs_on && !p.timers_on && b->use_order && b->n_filtered > 0) {
+  if (!pairs_on && !p.timers_on && (b->use_order == 2 || (b->use_order == 1 && b->n_filtered > 0))) {
     if (b->order_dirty) { const int rc_order = rebuild_order(b); if (rc_order) return rc_order; }
     if (b->n_order) {
       const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
@@ -326,8 +329,9 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
 }
 
 // lossless admission (reference: the sender blocks on a full channel, events/subscriber.go:30-32)
-int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) {
+int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok, uint32_t* prefix = nullptr) {
   *ok = true;
+  if (prefix) *prefix = n;
   if (!b->lossless || b->n_next == 0) return CPBUS_OK;
   // the most this launch can append to ONE mailbox: every event of the batch + every firing of its timer slots in the window
   uint64_t need = n;
@@ -336,17 +340,18 @@ int admit(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, bool* ok) 
     need += (uint64_t)b->K * per_slot;
   }
   if (b->room_lb >= need) { b->room_lb -= need; b->st.admit_skipped++; return CPBUS_OK; }   // provably fits: no kernel, no sync
-  CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, 3 * sizeof(unsigned long long), b->stream));   // overflow, overwritten, max_used
+  CK(cudaMemsetAsync(&b->d_stats->admit_overflow, 0, 4 * sizeof(unsigned long long), b->stream));   // overflow, overwritten, max_used, deficit
   const uint32_t threads = 256, grid = (b->n_next + threads - 1) / threads;
   admit_kernel<<<grid, threads, 0, b->stream>>>(d_src, n, w, b->d_ctl, b->d_timers, b->n_next, b->R, b->K,
                                                 b->cfg.sub_id_base, b->n_timers > 0 && b->K > 0, b->d_stats,
                                                 b->n_paired > 0 ? b->d_pairs : nullptr);
   CK(cudaGetLastError());
   b->st.kernel_launches++; b->st.admit_passes++;
-  CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, 3 * sizeof(unsigned long long),
+  CK(cudaMemcpyAsync(&b->h_stats->admit_overflow, &b->d_stats->admit_overflow, 4 * sizeof(unsigned long long),
                      cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   *ok = b->h_stats->admit_overflow == 0;
+  if (!*ok && prefix) *prefix = n - (uint32_t)std::min<unsigned long long>(n, b->h_stats->admit_deficit);   // events every mailbox can still take
   const uint64_t used = b->h_stats->admit_max_used;            // fullest mailbox, this batch included
   // admitted: the batch is in; refused: nothing was appended, so the fullest mailbox holds at most `used` minus its share (>= 0):
   // keep the conservative figure either way
@@ -405,9 +410,25 @@ int flush_staged(cpbus* b, uint64_t w) {
     if (!landed) CK(cudaStreamWaitEvent(b->stream, b->h2d_done[c], 0));
   }
   bool ok = true;
-  rc = admit(b, d_dst, n, w, &ok);
+  uint32_t m = n;
+  rc = admit(b, d_dst, n, w, &ok, &m);
   if (rc) return rc;
-  if (!ok) return CPBUS_EAGAIN;   // staged events stay staged; drain and call flush again
+  if (!ok) {
+    // Some mailbox lacks the room.  Like the Go bus, which blocks at the first event a full channel cannot take
+    // (events/subscriber.go:30-32), deliver the longest prefix EVERY mailbox can take — with the ticks due by its last
+    // event — keep the rest staged and report the stall; the caller lets the consumers run and flushes again.
+    if (m == 0) return CPBUS_EAGAIN;
+    const uint64_t w_part = b->h_batch[c][m - 1].ts_ns;
+    rc = launch_fanout(b, d_dst, m, w_part);
+    if (rc) return rc;
+    if (slot % cpbus::kDevEpoch == cpbus::kDevEpoch - 1) CK(cudaEventRecord(b->epoch_done[slot / cpbus::kDevEpoch], b->stream));
+    b->dev_slot = (slot + 1) % cpbus::kDevSlots;
+    memmove(b->h_batch[c], b->h_batch[c] + m, (size_t)(n - m) * sizeof(cpbus_event));   // (the H2D of this buffer completed before the admission pass)
+    b->n_staged = n - m;
+    b->room_lb = 0;
+    b->st.admit_partial++;
+    return CPBUS_EAGAIN;
+  }
   rc = launch_fanout(b, d_dst, n, w);
   if (rc) return rc;
   if (slot % cpbus::kDevEpoch == cpbus::kDevEpoch - 1) CK(cudaEventRecord(b->epoch_done[slot / cpbus::kDevEpoch], b->stream));
@@ -509,7 +530,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->room_lb = R;
   b->store = cfg->store_path == CPBUS_STORE_AUTO ? CPBUS_STORE_V8 : (int)cfg->store_path;
   if (const char* e = getenv("CPBUS_H2D_SPIN_US")) b->h2d_spin_us = atoi(e);
-  if (const char* e = getenv("CPBUS_ORDER")) b->use_order = atoi(e) != 0;
+  if (const char* e = getenv("CPBUS_ORDER")) b->use_order = atoi(e);
   if (const char* e = getenv("CPBUS_PDL")) b->pdl = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_ZERO_COPY")) b->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);

@@ -50,6 +50,11 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef CPBUS_ORD_PF
 #define CPBUS_ORD_PF 0       // (measured: -1.3 % on config 5) ORDERED build: prefetch.L2 of the whole block's control blocks once the ids are known
 #endif
+#ifndef CPBUS_ORD_RUNS
+#define CPBUS_ORD_RUNS 0     // ORDERED build: process runs of equal masks as a unit (records read once, stored to every ring of the run).
+                             // Measured (profiles/r02_ab_kernel_variants.md, table 5): bit-exact, but 5.7 % SLOWER on config 5 — the rings then
+                             // receive 1-2 KiB per visit instead of one contiguous 7.7 KiB append, and that costs more than the saved gathers.
+#endif
 constexpr uint32_t kActiveBit = 0x80000000u;   // mask word: subscriber is subscribed
 constexpr int kTimerHintShift = 24;            // mask word bits 24..27: #timer slots to look at
 constexpr uint32_t kPairBit = 0x10000000u;     // mask word bit 28: subscriber has a {code, source} pair table
@@ -87,7 +92,7 @@ struct DevStats {
   DevStatSlot slot[kStatSlots];
   unsigned long long admit_overflow, overwritten;
   unsigned long long admit_max_used;   // lossless admission: max over mailboxes of (undrained records + what the batch would append)
-  unsigned long long pad;
+  unsigned long long admit_deficit;    // ... and max over the mailboxes that lack room of (n - longest event prefix they can take)
 };
 
 // Accounting of batches that reach the bus already in device memory (cpbus_publish_device*, cpbus_stream_fanout).  What
@@ -572,6 +577,107 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   // (the trigger comes after the wait so that a launch can never overlap its grand-parent: two descriptor buffers suffice)
   if (!p.batch_dep) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
+  // ================= ORDERED build, no unicast in the batch: whole RUNS of equal masks at a time =================
+  // The warp's block is <= 32 consecutive positions of the mask order; lane l owns position pos + l for the whole block
+  // (its id is in my_ids, its control block in registers: ONE load instruction brings the block's control blocks in).
+  // A run of L mailboxes with the same mask word shares the filter pass AND the record reads: each gathered record is
+  // stored to all L rings back to back, so the index-list -> gather -> select chain is paid once per run, not per mailbox
+  // (round 2 ncu: that chain held 29 % of config 5's stall samples; DRAM throughput 70 % against 79 % for the dense paths).
+  bool runs_done = false;
+  if constexpr (ORDERED && !TIMERS && !PAIRS && CPBUS_ORD_RUNS) {
+    if (!s_dsum[1]) {   // CTA-uniform: no unicast record in this batch
+      runs_done = true;
+      const uint32_t present_r = s_dsum[0];
+      const uint32_t Rm_r = p.ring_cap - 1;
+      const uint4* s4r = reinterpret_cast<const uint4*>(s_batch);
+      const uint32_t swr = ((uint32_t)lane >> 2) & 1u;
+      uint16_t* my_idx = reinterpret_cast<uint16_t*>(s_tick + warp * max(32u, cap / 2u));
+      const uint32_t nb = pos < pos_end ? pos_end - pos : 0u;
+      const bool mine = (uint32_t)lane < nb;
+      uint4 ma = make_uint4(0, 0, 0, 0), mb = ma;
+      if (mine) ld_sector(p.ctl + my_ids, ma, mb, keep);
+      const uint32_t my_m = mine ? mb.z : 0u;
+      const uint64_t p32 = s_pow[32];
+      uint32_t j = 0;
+      while (j < nb) {
+        const uint32_t m = __shfl_sync(0xffffffffu, my_m, j);
+        if (!(m & kActiveBit)) { j++; continue; }
+        const uint32_t eq = __ballot_sync(0xffffffffu, mine && my_m == m) >> j;          // bit 0 = lane j itself
+        const uint32_t L = (eq == 0xffffffffu) ? 32u : (uint32_t)__ffs(~eq) - 1u;          // consecutive mailboxes with this mask word
+        const bool dense = (m & present_r) == present_r;
+        uint32_t k = n;
+        if (!dense) {   // pass 1: ballot 32 events at a time; matching lanes append their event index to the warp's scratch list
+          uint32_t base = 0;
+          const uint32_t nchunks = (n + 31) >> 5;
+          for (uint32_t c0 = 0; c0 < nchunks; c0 += 4) {
+            uint32_t cbit[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+              const uint32_t i = (c0 + u) * 32 + lane;
+              cbit[u] = i < n ? s_meta[i].x : 0u;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+              const bool match = (m & cbit[u]) != 0;
+              const uint32_t w = __ballot_sync(0xffffffffu, match);
+              if (match) my_idx[base + __popc(w & ((1u << lane) - 1u))] = (uint16_t)((c0 + u) * 32 + lane);
+              base += __popc(w);
+            }
+          }
+          k = base;
+          __syncwarp();
+        }
+        // pass 2: lane -> output slot; every record read once, stored to the L rings of the run
+        uint64_t acc = 0;
+        for (uint32_t o0 = 0; o0 < k; o0 += 64) {   // warp-uniform trip count (the shuffles below need every lane)
+          const uint32_t o = o0 + lane;
+          const bool v0 = o < k, v1 = o + 32 < k;
+          uint32_t i0 = o, i1 = o + 32;
+          if (!dense) { i0 = v0 ? my_idx[o] : 0u; i1 = v1 ? my_idx[o + 32] : 0u; }
+          uint4 a0, b0, a1, b1;
+          if (v0) lds_record<true>(s4r, i0, swr, a0, b0);
+          if (v1) lds_record<true>(s4r, i1, swr, a1, b1);
+          if (DIGEST && !dense) {
+            if (v0) acc = acc * p32 + s_rhash[i0];
+            if (v1) acc = acc * p32 + s_rhash[i1];
+          }
+#pragma unroll 2
+          for (uint32_t t = j; t < j + L; t++) {
+            const uint32_t tl = __shfl_sync(0xffffffffu, ma.x, t);                        // low word of the tail: all the ring index needs
+            const uint32_t id = __shfl_sync(0xffffffffu, my_ids, t);
+            cpbus_event* ring = p.ring + (size_t)id * p.ring_cap;
+            if (v0) st_record<STORE>(ring + ((tl + o) & Rm_r), a0, b0);
+            if (v1) st_record<STORE>(ring + ((tl + o + 32) & Rm_r), a1, b1);
+          }
+        }
+        uint64_t dsum = 0;
+        if (DIGEST && k) {
+          if (dense) dsum = s_q[n];
+          else {   // per-lane Horner in P^32, then one power per lane: lane l wrote outputs l, l+32, ...; its last one is o_last
+            const uint32_t cnt = k > (uint32_t)lane ? (k - lane + 31u) / 32u : 0u;
+            dsum = cnt ? acc * s_pow[k - 1 - (lane + 32u * (cnt - 1u))] : 0ull;
+            dsum = warp_sum64(dsum);
+          }
+        }
+        if (k && (uint32_t)lane >= j && (uint32_t)lane < j + L) {   // each lane of the run writes ITS mailbox's control block back
+          const uint64_t tail = ((uint64_t)ma.y << 32) | ma.x, dig = ((uint64_t)mb.y << 32) | mb.x;
+          const uint64_t nt = tail + k;
+          const uint64_t nd = DIGEST ? dig * s_pow[k] + dsum : dig;
+          st_sector(p.ctl + my_ids, make_uint4((uint32_t)nt, (uint32_t)(nt >> 32), ma.z, ma.w),
+                    make_uint4((uint32_t)nd, (uint32_t)(nd >> 32), mb.z, 0u), keep);
+          atomicAdd(&s_sum->acc_deliv, k);
+          if (DIGEST) {
+            const uint32_t f = (uint32_t)nd ^ (uint32_t)(nd >> 32);
+            atomicAdd(&s_sum->acc_dig_lo, f & 0xFFFFu);
+            atomicAdd(&s_sum->acc_dig_hi, f >> 16);
+          }
+        }
+        __syncwarp();   // my_idx is rewritten by the next run's pass 1
+        j += L;
+      }
+    }
+  }
+  if (runs_done) pos = pos_end;   // nothing left for the per-mailbox loop below
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
   if (pos < pos_end) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
     ld_sector(p.ctl + s, ca, cb, keep);
@@ -1108,7 +1214,40 @@ __global__ void admit_kernel(const cpbus_event* batch, uint32_t n_ev, uint64_t w
         k += tm.period ? (w_now - tm.next_due) / tm.period + 1u : 1u;
     }
     const unsigned long long used = c.tail - c.head + k;
-    if (used > ring_cap) atomicAdd(&stats->admit_overflow, 1ull);
+    if (used > ring_cap) {
+      atomicAdd(&stats->admit_overflow, 1ull);
+      // Per-event blocking (events/subscriber.go:30-32: the publisher stalls at the FIRST event a full channel cannot take):
+      // the longest prefix of the batch this mailbox has room for, its share of the ticks due by then included.  Events are
+      // sorted by ts; a tick due at d sits in front of the first event with ts >= d.
+      const unsigned long long room = ring_cap - min((unsigned long long)ring_cap, c.tail - c.head);
+      const uint32_t gid = sub_base + s;
+      unsigned long long taken = 0;
+      uint32_t prefix = 0;
+      for (uint32_t i = 0; i < n_ev; i++) {
+        const cpbus_event e = batch[i];
+        unsigned long long tks = 0;
+        for (uint32_t t = 0; t < nslots; t++) {
+          const DevTimer tm = timers[(size_t)s * K + t];
+          if (tm.next_due != kTimerIdle && tm.next_due <= e.ts_ns) tks += tm.period ? (e.ts_ns - tm.next_due) / tm.period + 1u : 1u;
+        }
+        bool want;
+        if (e.target == CPBUS_TARGET_ALL) {
+          want = e.code < CPBUS_N_CODES && ((m >> e.code) & 1u);
+          if (!want && pairs && (m & kPairBit)) {
+            const uint2* my = pairs + (size_t)s * CPBUS_MAX_PAIRS;
+            for (uint32_t j = 0; j < CPBUS_MAX_PAIRS && !want; j++) {
+              const uint2 pr = my[j];
+              if (pr.x == kPairNone) break;
+              want = pr.x == e.code && pr.y == e.source_id;
+            }
+          }
+        } else want = e.target == gid;
+        if (taken + (want ? 1u : 0u) + tks > room) break;
+        taken += want ? 1u : 0u;
+        prefix = i + 1;
+      }
+      atomicMax(&stats->admit_deficit, (unsigned long long)(n_ev - prefix));
+    }
     atomicMax(&s_max, used);
   }
   // how full the fullest mailbox would be after this batch: lets the host skip the admission pass (and its sync) for the

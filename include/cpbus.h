@@ -135,6 +135,7 @@ typedef struct cpbus_stats_t {
   uint64_t ephemeral_recycled; /* ephemeral ids that have been recycled so far   */
   uint64_t admit_passes;   /* lossless mode: flushes that needed the admission kernel (+ one host sync) ... */
   uint64_t admit_skipped;  /* ... and flushes that provably fitted and went straight to the fan-out        */
+  uint64_t admit_partial;  /* flushes that delivered only the prefix every mailbox could take (then EAGAIN)  */
 } cpbus_stats_t;
 
 typedef struct cpbus cpbus_t;
@@ -193,8 +194,12 @@ int cpbus_timer_cancel(cpbus_t* bus, uint32_t timer_id);
  * Lossless mode: if an automatic flush hits a full mailbox the call stops and returns
  * CPBUS_EAGAIN; events before the one that triggered the flush are staged, that one and
  * the rest are not (cpbus_stats.publishes tells how many were taken).  Publishing one
- * event per call, as the Go bus does, makes the retry point unambiguous.  Admission is
- * all-or-nothing per batch: nothing of a refused batch is delivered. */
+ * event per call, as the Go bus does, makes the retry point unambiguous.  cpbus_flush in
+ * lossless mode blocks PER EVENT like the Go bus: when some mailbox lacks the room, the longest
+ * prefix of the staged events that every targeted mailbox can take is delivered (with the timer
+ * ticks due by its last event), the rest stays staged and the call returns CPBUS_EAGAIN; after the
+ * consumers have drained, the next flush continues with the first undelivered event.
+ * (cpbus_publish_device / cpbus_send batches handed over in device memory stay all-or-nothing.) */
 int cpbus_publish(cpbus_t* bus, const cpbus_event* ev, size_t n);
 /* Direct mailbox write, bypassing the filter (`job.Rx <- ev`, jobs/jobs.go:262;
  * Subscriber.Receive, events/subscriber.go:30).  Ordered with publishes. */
