@@ -199,7 +199,7 @@ int cpbus_timer_cancel(cpbus_t* bus, uint32_t timer_id);
  * prefix of the staged events that every targeted mailbox can take is delivered (with the timer
  * ticks due by its last event), the rest stays staged and the call returns CPBUS_EAGAIN; after the
  * consumers have drained, the next flush continues with the first undelivered event.
- * (cpbus_publish_device / cpbus_send batches handed over in device memory stay all-or-nothing.) */
+ * (Batches handed over in device memory, cpbus_publish_device, stay all-or-nothing: the caller owns them.) */
 int cpbus_publish(cpbus_t* bus, const cpbus_event* ev, size_t n);
 /* Direct mailbox write, bypassing the filter (`job.Rx <- ev`, jobs/jobs.go:262;
  * Subscriber.Receive, events/subscriber.go:30).  Ordered with publishes. */

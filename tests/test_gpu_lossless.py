@@ -81,3 +81,53 @@ def test_device_consumer_keeps_lossless_mode_on_the_fast_path():
         st = bus.stats()
         assert st["admit_passes"] == 0 and st["admit_skipped"] == 30
         assert len(bus.drain(5)) == 0                               # everything was consumed on the device
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_flush_blocks_per_event_like_the_go_bus(seed):
+    """The Go publisher stalls at the FIRST event a full channel cannot take (events/subscriber.go:30-32); everything in front
+    of it has been delivered.  The oracle models exactly that (mailbox_cap: orc_publish refuses one event at a time).  The
+    GPU bus publishes whole batches: when cpbus_flush returns EAGAIN, every mailbox must hold exactly what the oracle's
+    mailboxes hold at ITS stall point — the longest prefix every targeted mailbox could take — and the next flush continues
+    with the first undelivered event."""
+    R, B, N = 128, 64, 6
+    rng = np.random.default_rng(100 + seed)
+    masks = [nat.MASK_ALL, 1 << 2, (1 << 3) | (1 << 2), nat.MASK_ALL, 1 << 5, 0]
+    orc = ob.Oracle(N, keep_window=0, mailbox_cap=R)
+    for m_ in masks:
+        orc.subscribe(m_)
+    with Bus(N, ring_cap=R, batch_cap=B, lossless=True) as bus:
+        bus.subscribe_many(np.array(masks, dtype=np.uint32))
+        got = [[] for _ in range(N)]
+        n_partial = 0
+        for step in range(60):
+            ev = np.zeros(B, dtype=EVENT_DTYPE)
+            ev["code"] = rng.integers(1, 7, B); ev["source_id"] = step * B + np.arange(B)
+            nat.check(bus.publish_many(ev), "publish")
+            i = 0
+            while True:
+                rc = bus.flush()
+                while i < B:                                          # the oracle publishes event by event until it blocks
+                    r = orc.publish(int(ev["code"][i]), int(ev["source_id"][i]))
+                    if r == ob.EAGAIN:
+                        break
+                    assert r == 0
+                    i += 1
+                counts = bus.digests(0, N)["count"]
+                assert [int(c) for c in counts] == [orc.count(s) for s in range(N)], (step, i, rc)   # same delivered sets at the stall point
+                if rc == nat.OK:
+                    assert i == B
+                    break
+                assert rc == nat.EAGAIN and i < B
+                n_partial += 1 if i > 0 else 0
+                for s in rng.permutation(N)[:3]:                      # some consumers run (not necessarily the full one)
+                    take = int(rng.integers(1, R + 1))
+                    g = bus.drain(int(s), cap=take)
+                    o = orc.consume(int(s), take)
+                    assert g.tobytes() == o.tobytes()
+                    got[int(s)].append(g)
+        for s in range(N):
+            g = bus.drain(s, cap=R); o = orc.consume(s, R)
+            assert g.tobytes() == o.tobytes()
+        st = bus.stats()
+        assert st["admit_partial"] > 0 and n_partial > 0 and st["overwritten"] == 0
