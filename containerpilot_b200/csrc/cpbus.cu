@@ -39,6 +39,32 @@ thread_local char g_cuda_err[256] = "";
 // debug ring entry awaiting enqueue: a concrete event, or "the broadcast events of device launch `launch`"
 struct DbgItem { bool marker; unsigned long long launch; cpbus_event ev; };
 
+// publish counts by (code << 32 | source_id): the label set of `containerpilot_events` (events/bus.go:131).  Flat
+// open-addressing table (key + 1 stored, 0 = empty): an increment is one probe in the common case, and a burst of n
+// events is counted in two passes (slots prefetched, then incremented) so that cache misses of a high-cardinality
+// source set overlap instead of adding up (a std::unordered_map here cost ~40 ns per published event).
+struct PairCounter {
+  std::vector<uint64_t> keys, cnts;
+  size_t used = 0;
+  static uint64_t mix(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; return k; }
+  void grow() {
+    std::vector<uint64_t> ok, oc;
+    ok.swap(keys); oc.swap(cnts);
+    const size_t cap = ok.empty() ? 1024 : ok.size() * 2;
+    keys.assign(cap, 0); cnts.assign(cap, 0); used = 0;
+    for (size_t i = 0; i < ok.size(); i++) if (ok[i]) add(ok[i] - 1, oc[i]);
+  }
+  void add(uint64_t key, uint64_t by) {
+    if ((used + 1) * 2 > keys.size()) grow();
+    const size_t mask = keys.size() - 1;
+    for (size_t i = mix(key) & mask;; i = (i + 1) & mask) {
+      if (keys[i] == key + 1) { cnts[i] += by; return; }
+      if (!keys[i]) { keys[i] = key + 1; cnts[i] = by; used++; return; }
+    }
+  }
+  void prefetch(uint64_t key) const { if (!keys.empty()) { const size_t i = mix(key) & (keys.size() - 1); __builtin_prefetch(&keys[i]); __builtin_prefetch(&cnts[i]); } }
+};
+
 struct HostTimer { bool active = false, oneshot = false; uint8_t gen = 0; uint64_t period = 0, next_due = 0; uint32_t source_id = 0; };
 // timer id = slot index (subscriber * K + k) | generation << 26: a late cancel from an old context cannot disarm a re-armed slot
 constexpr uint32_t kTimerSlotBits = 26, kTimerSlotMask = (1u << kTimerSlotBits) - 1u;
@@ -83,7 +109,7 @@ struct cpbus {
   DevPubAcct* d_acct = nullptr;
   DevPubAcct* h_acct = nullptr;               // pinned staging for cpbus_stats / cpbus_debug_events / cpbus_publish_counts
   std::deque<DbgItem> dbg_pending;            // debug-ring entries not yet enqueued (events, or markers of device batches)
-  std::unordered_map<uint64_t, uint64_t> pub_pairs;   // host publishes by (code << 32 | source_id), Metric excluded (bus.go:130-132)
+  PairCounter pub_pairs;                              // host publishes by (code << 32 | source_id), Metric excluded (bus.go:130-132)
   cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
@@ -302,6 +328,10 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
       const uint32_t warps = (b->n_order + spw - 1) / spw;
       grid = std::max(1u, (warps + kWarpsPerCta - 1) / kWarpsPerCta);
     }
+  }
+  if (pairs_on && !b->cfg.grid_ctas) {   // PAIRS build: lane-parallel triage over blocks of 32 mailboxes per warp turn
+    const uint32_t blocks = (b->n_next + 31u) / 32u;
+    grid = std::max(1u, std::min((blocks + kWarpsPerCta - 1) / kWarpsPerCta, (uint32_t)b->sm_count * 16u));
   }
   const int variant = pairs_on ? (p.use_digest ? 7 : 6) : (p.timers_on ? 2 : 0) | (p.use_digest ? 1 : 0) | (p.order ? 4 : 0);
 #define CPBUS_DISPATCH(ST)                                                                \
@@ -931,18 +961,29 @@ int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
 int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) {
   if (!b || (!ev && n)) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {   // counter slots of the whole burst: requested up front, touched in the loop below
+    if (ev[i].code < CPBUS_N_CODES && ev[i].code != CPBUS_METRIC) b->pub_pairs.prefetch(((uint64_t)ev[i].code << 32) | ev[i].source_id);
+  }
+  // The debug ring holds 10 entries (events/bus.go:24-31): of a burst only the last 10 published can ever be seen, so only
+  // those are enqueued — including when the call stops early (CPBUS_EAGAIN from an automatic flush in lossless mode).
+  auto dbg_tail = [&](size_t published) {
+    for (size_t j = published > 10 ? published - 10 : 0; j < published; j++) {
+      cpbus_event e{};
+      e.seq = b->seq - (published - j); e.ts_ns = b->now; e.code = ev[j].code; e.source_id = ev[j].source_id; e.target = CPBUS_TARGET_ALL;
+      dbg_enqueue(b, e);
+    }
+  };
+  for (size_t i = 0; i < n; i++) if (ev[i].code >= CPBUS_N_CODES) return CPBUS_EINVAL;   // nothing of an invalid burst is published
   for (size_t i = 0; i < n; i++) {
     const uint32_t code = ev[i].code;
-    if (code >= CPBUS_N_CODES) return CPBUS_EINVAL;
-    if ((rc = stage_one(b, code, ev[i].source_id, CPBUS_TARGET_ALL, 0))) return rc;
-    const cpbus_event& e = b->h_batch[b->cur][b->n_staged - 1];
+    if ((rc = stage_one(b, code, ev[i].source_id, CPBUS_TARGET_ALL, 0))) { dbg_tail(i); return rc; }
     if (code != CPBUS_METRIC) {                                  // events/bus.go:130-132
       b->st.published_by_code[code]++;
-      b->pub_pairs[((uint64_t)code << 32) | ev[i].source_id]++;
+      b->pub_pairs.add(((uint64_t)code << 32) | ev[i].source_id, 1);
     }
-    dbg_enqueue(b, e);                                           // events/bus.go:139
     b->st.publishes++;
   }
+  dbg_tail(n);                                                   // events/bus.go:139
   return CPBUS_OK;
 }
 
@@ -1539,7 +1580,8 @@ int cpbus_publish_counts(cpbus_t* b, cpbus_pair_count* out, size_t cap, size_t* 
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
-  std::unordered_map<uint64_t, uint64_t> merged = b->pub_pairs;
+  std::unordered_map<uint64_t, uint64_t> merged;
+  for (size_t i = 0; i < b->pub_pairs.keys.size(); i++) if (b->pub_pairs.keys[i]) merged[b->pub_pairs.keys[i] - 1] += b->pub_pairs.cnts[i];
   if (b->launch_seq) {
     std::vector<unsigned long long> keys(kAcctPairSlots), cnts(kAcctPairSlots);
     CK(cudaMemcpyAsync(keys.data(), b->d_acct->pair_key, sizeof(unsigned long long) * kAcctPairSlots, cudaMemcpyDeviceToHost, b->stream));

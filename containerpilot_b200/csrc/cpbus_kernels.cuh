@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
   const bool timers_on = TIMERS && p.timers_on && K;
   const uint32_t wstride = gridDim.x * kWarpsPerCta;
-  const uint32_t pos_end = aborted ? 0u : (ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs);
+  uint32_t pos_end = aborted ? 0u : (ORDERED ? min(pos + p.spw, p.n_order) : p.n_subs);
   const uint32_t pos_step = ORDERED ? 1u : wstride;
   const uint32_t pos0 = pos;
   uint32_t s = ORDERED ? __shfl_sync(0xffffffffu, my_ids, 0) : pos;
@@ -679,18 +679,73 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
   }
   if (runs_done) pos = pos_end;   // nothing left for the per-mailbox loop below
   uint4 ca = make_uint4(0, 0, 0, 0), cb = ca, ta = ca;
-  if (pos < pos_end) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
+  if (!PAIRS && pos < pos_end) {   // software pipeline, stage 0: first subscriber's control block (and timer slot)
     ld_sector(p.ctl + s, ca, cb, keep);
     if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
   }
   const uint32_t present = s_dsum[0];
   const bool has_unicast = s_dsum[1] != 0;
+  // PAIRS build: TRIAGE.  A fleet of pair-filtered subscribers (jobs/jobs.go:188-231: every consumer listens for a dozen exact
+  // events) takes almost nothing from a given batch, so walking the mailboxes one per warp-iteration — control block, then
+  // pair table, then 16 probes, each a dependent load — is all latency (round 2 ncu: 46 us per launch for 32,768 mailboxes
+  // and 55 deliveries).  Instead lane l decides for mailbox 32*blk + l: one control-block load per lane, and only when the
+  // code mask misses, its timer slots' due times and its pair row's probes into the presence filter.  The ballot of the
+  // survivors drives the ordinary per-mailbox path below (control block handed over by shuffles); exactness is unchanged —
+  // a survivor may still turn out to receive nothing.
+  bool bulk_pending = false;
+  uint32_t tri_blk = blockIdx.x * kWarpsPerCta + warp, tri_base = 0, tri_live = 0;
+  uint4 tri_a = make_uint4(0, 0, 0, 0), tri_b = tri_a;
+  for (;;) {   // PAIRS: one surviving mailbox per turn; every other build: exactly one turn
+  if constexpr (PAIRS) {
+    bool exhausted = aborted;
+    while (!tri_live && !exhausted) {
+      tri_base = tri_blk * 32u;
+      if (tri_base >= p.n_subs) { exhausted = true; break; }
+      tri_blk += wstride;
+      const uint32_t sl = tri_base + lane;
+      bool live = false;
+      tri_a = make_uint4(0, 0, 0, 0); tri_b = tri_a;
+      if (sl < p.n_subs) ld_sector(p.ctl + sl, tri_a, tri_b, keep);
+      const uint32_t ml = tri_b.z;
+      if (ml & kActiveBit) {
+        live = has_unicast || (ml & present) != 0;
+        if (!live && timers_on) {
+          const uint32_t nsl = min((ml >> kTimerHintShift) & 0xFu, K);
+          for (uint32_t t = 0; t < nsl && !live; t++) {
+            uint4 h;
+            ld_half(p.timers + (size_t)sl * K + t, h, keep);
+            const uint64_t due = ((uint64_t)h.y << 32) | h.x;
+            live = due != kTimerIdle && due <= p.w_now;
+          }
+        }
+        if (!live && (ml & kPairBit)) {
+          const uint4* row = reinterpret_cast<const uint4*>(p.pairs + (size_t)sl * CPBUS_MAX_PAIRS);
+          for (uint32_t q = 0; q < CPBUS_MAX_PAIRS / 2 && !live; q++) {
+            const uint4 v = __ldg(row + q);                      // two {code, source} cases
+            if (v.x >= 32u) break;                               // used slots come first
+            uint32_t h = pair_key_hash(v.x, v.y);
+            live = ((s_present[(h & 32767u) >> 5] >> (h & 31u)) & (s_present[((h >> 15) & 32767u) >> 5] >> ((h >> 15) & 31u)) & 1u) != 0;
+            if (live || v.z >= 32u) { if (!live) break; continue; }
+            h = pair_key_hash(v.z, v.w);
+            live = ((s_present[(h & 32767u) >> 5] >> (h & 31u)) & (s_present[((h >> 15) & 32767u) >> 5] >> ((h >> 15) & 31u)) & 1u) != 0;
+          }
+        }
+      }
+      tri_live = __ballot_sync(0xffffffffu, live);
+    }
+    if (exhausted) break;
+    const uint32_t jl = (uint32_t)__ffs(tri_live) - 1u;
+    tri_live &= tri_live - 1u;
+    pos = tri_base + jl; pos_end = pos + 1u; s = pos;
+    ca = make_uint4(__shfl_sync(0xffffffffu, tri_a.x, jl), __shfl_sync(0xffffffffu, tri_a.y, jl), __shfl_sync(0xffffffffu, tri_a.z, jl), __shfl_sync(0xffffffffu, tri_a.w, jl));
+    cb = make_uint4(__shfl_sync(0xffffffffu, tri_b.x, jl), __shfl_sync(0xffffffffu, tri_b.y, jl), __shfl_sync(0xffffffffu, tri_b.z, jl), __shfl_sync(0xffffffffu, tri_b.w, jl));
+    if (timers_on && tk_slot < K) ld_half(p.timers + (size_t)s * K + tk_slot, ta, keep);
+  }
   const uint32_t Rm = p.ring_cap - 1;
   const uint4* s4 = reinterpret_cast<const uint4*>(s_batch);
   const uint32_t sw = ((uint32_t)lane >> 2) & 1u;                      // which half this lane fetches first (lds_record)
   const uint32_t scratch_words = max(32u, cap / 2u);                   // per warp: 32 tick positions or cap u16 event indices
   uint32_t* my_tick = s_tick + warp * scratch_words;
-  bool bulk_pending = false;
 
   // software pipeline: the control block (and timer slot) of the NEXT subscriber is in flight
   // while the current one is being written, so no DRAM round trip is exposed per subscriber
@@ -1085,6 +1140,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     }
   }
 
+  if constexpr (!PAIRS) break;
+  }   // triage turns
   if (STORE == CPBUS_STORE_BULK && bulk_pending && lane == 0)
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged batch must outlive the TMA reads
   __syncthreads();
