@@ -50,6 +50,9 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef CPBUS_ORD_PF
 #define CPBUS_ORD_PF 0       // (measured: -1.3 % on config 5) ORDERED build: prefetch.L2 of the whole block's control blocks once the ids are known
 #endif
+#ifndef CPBUS_IDX_PF
+#define CPBUS_IDX_PF 1       // filtered path, pass 2: read the index list one iteration ahead (measured: -0.35 % on config 5)
+#endif
 #ifndef CPBUS_ORD_RUNS
 #define CPBUS_ORD_RUNS 0     // ORDERED build: process runs of equal masks as a unit (records read once, stored to every ring of the run).
                              // Measured (profiles/r02_ab_kernel_variants.md, table 5): bit-exact, but 5.7 % SLOWER on config 5 — the rings then
@@ -981,6 +984,27 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         const uint64_t p32 = s_pow[32];
         const bool hashing = DIGEST && !reuse;
         uint32_t o = lane;
+#if CPBUS_IDX_PF
+        // the index list is read one iteration ahead: the records' shared-memory addresses are then ready when the loop turns
+        uint32_t i0 = o < k ? my_idx[o] : 0u, i1 = o + 32 < k ? my_idx[o + 32] : 0u;
+        for (; o + 32 < k; o += 64) {
+          const uint32_t n0 = o + 64 < k ? my_idx[o + 64] : 0u, n1 = o + 96 < k ? my_idx[o + 96] : 0u;
+          uint4 a0, b0, a1, b1;
+          lds_record<ORDERED>(s4, i0, sw, a0, b0);
+          lds_record<ORDERED>(s4, i1, sw, a1, b1);
+          st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
+          st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
+          if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
+          i0 = n0; i1 = n1;
+        }
+        if (o < k) {
+          uint4 a, b;
+          lds_record<ORDERED>(s4, i0, sw, a, b);
+          st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
+          if (hashing) acc = acc * p32 + s_rhash[i0];
+          o += 32;
+        }
+#else
         for (; o + 32 < k; o += 64) {   // two outputs per lane per iteration: their index/record/hash loads are independent
           const uint32_t i0 = my_idx[o], i1 = my_idx[o + 32];
           uint4 a0, b0, a1, b1;
@@ -997,6 +1021,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
           if (hashing) acc = acc * p32 + s_rhash[i];
         }
+#endif
         if (DIGEST) {
           if (reuse) dsum = run_sum;
           else {
