@@ -316,7 +316,8 @@ int cpbus_debug_events(cpbus_t* bus, cpbus_event* out, size_t cap, size_t* n);
 int cpbus_stats(cpbus_t* bus, cpbus_stats_t* out);
 /* Publish counts by {code, source}: the label set of the reference's `containerpilot_events` counter
  * (events/bus.go:60-68,130-132; code Metric is excluded there and here).  Covers both host publishes and batches that
- * reached the bus in device memory (counted by the kernel).  Writes at most cap entries, *n = entries available. */
+ * reached the bus in device memory (counted by the kernel).  Writes at most cap entries, *n = entries available.
+ * Call it from the publisher's thread (or with the publisher quiescent): it reads the table cpbus_publish updates. */
 typedef struct cpbus_pair_count { uint32_t code, source_id; uint64_t count; } cpbus_pair_count;
 int cpbus_publish_counts(cpbus_t* bus, cpbus_pair_count* out, size_t cap, size_t* n);
 /* HBM layout, for zero-copy inspection by tests/bench: `ring` = n_max_subs mailboxes of
