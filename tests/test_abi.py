@@ -4,6 +4,7 @@ without a device the library refuses to run (no CPU fallback)."""
 import ctypes as C
 import json
 import os
+import subprocess
 import re
 
 import numpy as np
@@ -101,3 +102,25 @@ def test_create_rejects_bad_configs_before_touching_the_device():
     assert lib.cpbus_create(None, None) == nat.EINVAL
     assert lib.cpbus_destroy(None) == nat.EINVAL
     assert lib.cpbus_strerror(nat.EAGAIN).startswith(b"mailbox full")
+
+
+C_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+
+
+def build_c_smoke():
+    """tests/c/abi_smoke.c: the C-ABI called from plain C99 (what cgo-generated code does), -Wall -Wextra -Werror -pedantic"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(C_DIR, "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(C_DIR, "abi_smoke.c"), "-L", os.path.join(root, "containerpilot_b200"), "-lcpbus",
+                           "-Wl,-rpath," + os.path.join(root, "containerpilot_b200"), "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c99_and_a_c_caller_links():
+    exe = build_c_smoke()
+    assert os.path.exists(exe)
+    import torch
+    if not torch.cuda.is_available():            # without a device the program must stop at cpbus_create with ENODEV, loudly
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stdout
