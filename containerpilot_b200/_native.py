@@ -88,6 +88,7 @@ SYMBOLS = {
     "cpbus_stream_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, _P(C.c_void_p)]),
     "cpbus_stream_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32]),
     "cpbus_stream_fanout": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64]),
+    "cpbus_stream_poll": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_size_t), _P(C.c_uint64)]),
     "cpbus_stream_status": (C.c_int, [C.c_void_p]),
     "cpbus_stream_set_timeout": (C.c_int, [C.c_void_p, C.c_uint32]),
     "cpbus_stream_close": (C.c_int, [C.c_void_p]),

@@ -185,6 +185,12 @@ class Bus:
     def stream_fanout(self, st, n: int, now_ns: int) -> int:
         return self._lib.cpbus_stream_fanout(st, n, now_ns)
 
+    def stream_poll(self, st):
+        """(n, now_ns) of the next batch if the publisher has released it, else None — for consumers that are not told"""
+        ready, n, now = C.c_int(), C.c_size_t(), C.c_uint64()
+        nat.check(self._lib.cpbus_stream_poll(st, C.byref(ready), C.byref(n), C.byref(now)), "cpbus_stream_poll")
+        return (n.value, now.value) if ready.value else None
+
     def stream_status(self, st) -> int:
         return self._lib.cpbus_stream_status(st)
 

@@ -1308,6 +1308,22 @@ int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64
   return CPBUS_OK;
 }
 
+// Consumers that are NOT told n / now_ns by their driver: look at the next slot's header (one 32-byte copy across the link).
+// *ready = 0: the publisher has not released that batch yet.
+int cpbus_stream_poll(cpbus_stream_t* st, int* ready, size_t* n, uint64_t* now_ns) {
+  if (!st || !ready) return CPBUS_EINVAL;
+  cpbus* b = st->bus;
+  int rc = dev_guard(b); if (rc) return rc;
+  if (*(volatile unsigned int*)b->h_err) return CPBUS_ETIMEDOUT;
+  const unsigned long long q = st->get_seq + 1;
+  StreamHdr h{};
+  CK(cudaMemcpyAsync(&h, &st->hdr[q % st->n_slots], sizeof(h), cudaMemcpyDeviceToHost, b->result_stream));
+  CK(cudaStreamSynchronize(b->result_stream));
+  *ready = h.seq == q ? 1 : 0;
+  if (*ready) { if (n) *n = h.n; if (now_ns) *now_ns = h.watermark; }
+  return CPBUS_OK;
+}
+
 // Every rank (the publisher's included): fan out the next batch of the stream to this GPU's shard.
 int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns) {
   if (!st || n > st->B) return CPBUS_EINVAL;

@@ -244,8 +244,8 @@ int cpbus_publish_device_staged(cpbus_t* bus, const void* d_events, size_t n, ui
  *   other ranks    : cpbus_stream_open(bus, handle, consumer_index (1..n_consumers-1), &st)
  *   every step     : [publisher] cpbus_stream_put(st, events, n, now_ns, flags)   (may run ahead by < n_slots batches)
  *                    [all ranks] cpbus_stream_fanout(st, n, now_ns)
- * The consumers must be told n and now_ns of every batch by the caller (SPMD drivers know them; the header carries both
- * and the kernel cross-checks n).  CPBUS_EAGAIN from _put: the slot's previous batch is still not acknowledged by every
+ * The consumers must be told n and now_ns of every batch by the caller: SPMD drivers know them; others ask cpbus_stream_poll,
+ * which reads them from the slot header (the kernel cross-checks n either way).  CPBUS_EAGAIN from _put: the slot's previous batch is still not acknowledged by every
  * consumer after the stream timeout (or at once with CPBUS_PUT_NOWAIT) — call again after the consumers have advanced.  CPBUS_ETIMEDOUT from _fanout/_status: an earlier stream
  * launch gave up waiting for its batch (bounded in-kernel wait, cpbus_stream_set_timeout) and delivered nothing. */
 typedef struct cpbus_stream cpbus_stream_t;
@@ -264,6 +264,9 @@ int cpbus_stream_open(cpbus_t* bus, const unsigned char handle[64], uint32_t con
 int cpbus_stream_attach(cpbus_t* bus, cpbus_stream_t* owner, uint32_t consumer_index, cpbus_stream_t** out);
 int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* events, size_t n, uint64_t now_ns, uint32_t flags);
 int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns);
+/* For a consumer whose driver does not know the batches' shapes: *ready = 1 and {n, now_ns} of the NEXT batch if the publisher
+ * has released it, *ready = 0 otherwise (one 32-byte read of the slot header, synchronous).  Then cpbus_stream_fanout(st, n, now_ns). */
+int cpbus_stream_poll(cpbus_stream_t* st, int* ready, size_t* n, uint64_t* now_ns);
 int cpbus_stream_status(cpbus_stream_t* st);                       /* CPBUS_OK or the sticky error */
 int cpbus_stream_set_timeout(cpbus_stream_t* st, uint32_t microseconds);   /* in-kernel wait bound; default 2 s */
 int cpbus_stream_close(cpbus_stream_t* st);                        /* importers close before the owner */

@@ -111,6 +111,36 @@ def test_stream_ring_wraps_and_put_backpressure():
         sb.close()
 
 
+def test_consumer_that_is_not_told_the_shapes_polls_the_headers():
+    """cpbus_stream_poll: a consumer follows the publisher knowing nothing but the stream — ragged batches, clock from the header."""
+    N, B = 50, 64
+    batches = _batches(5, 12, B)
+    masks = np.full(N, nat.MASK_ALL, dtype=np.uint32)
+    sb = LocalShardedBus(N, _devices(2), ring_cap=1024, batch_cap=B, stream_slots=8)
+    try:
+        sb.subscribe_many(masks)
+        pub_bus, pub_st = sb.shards[0][2], sb._st[0]
+        con_bus, con_st = sb.shards[1][2], sb._st[1]
+        assert con_bus.stream_poll(con_st) is None                  # nothing released yet
+        for q, ev in enumerate(batches):
+            nat.check(sb.put(ev, (q + 1) * 7000), "put")
+            nat.check(pub_bus.stream_fanout(pub_st, len(ev), (q + 1) * 7000), "fanout")     # the publisher's own shard knows
+            shape = None                                            # the other one asks (the release is an asynchronous copy)
+            for _ in range(100_000):
+                shape = con_bus.stream_poll(con_st)
+                if shape is not None:
+                    break
+            assert shape == (len(ev), (q + 1) * 7000)
+            nat.check(con_bus.stream_fanout(con_st, *shape), "fanout")
+        assert con_bus.stream_poll(con_st) is None
+        sb.sync()
+        for first, count, bus in sb.shards:
+            orc = _oracle_for_shard(first, count, masks, batches, 7000, 0, 0)
+            tr.compare(bus, orc, count, sub_id_base=first)
+    finally:
+        sb.close()
+
+
 def test_stream_wait_is_bounded_and_reports_timeout():
     """A consumer launched for a batch the publisher never released gives up after the configured bound: the kernel ends,
     nothing is delivered, the bus reports CPBUS_ETIMEDOUT from then on."""
