@@ -111,3 +111,40 @@ def test_random_trace_is_deterministic_and_shard_invariant():
     for s in range(n_total):
         assert o1.digest(s) == o2.digest(s) and o1.count(s) == o2.count(s)
     assert o1.total_deliveries() > 1000
+
+
+def test_publish_records_equals_event_at_a_time_publishing():
+    """orc_publish_records (complete records, as cpbus_publish_device / CPBUS_PUT_RAW take them) is the same bus as
+    advance + publish / receive one event at a time: identical mailboxes, digests, debug ring and counters."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    n_subs, n_ev = 9, 600
+    masks = [0x1FFFF if rng.random() < 0.4 else int(rng.integers(0, 1 << 17)) for _ in range(n_subs)]
+    a = ob.Oracle(n_subs, timers_per_sub=2); b = ob.Oracle(n_subs, timers_per_sub=2)
+    for o in (a, b):
+        for s, m in enumerate(masks):
+            o.subscribe(m)
+            o.timer_add(s, 700 + 13 * s, 500 + s, False)
+            if s % 3 == 0:
+                o.timer_add(s, 2000, 900 + s, True)
+    rec = np.zeros(n_ev, dtype=ob.EVENT_DTYPE)
+    rec["seq"] = np.arange(n_ev); rec["ts_ns"] = np.cumsum(rng.integers(0, 40, n_ev)) + 1
+    rec["code"] = rng.integers(0, 17, n_ev); rec["source_id"] = rng.integers(0, 30, n_ev); rec["target"] = 0xFFFFFFFF
+    uni = rng.random(n_ev) < 0.05
+    rec["target"][uni] = rng.integers(0, n_subs, int(uni.sum())); rec["flags"][uni] = 2
+    for lo in range(0, n_ev, 50):
+        chunk = rec[lo:lo + 50]
+        assert a.publish_records(chunk, int(chunk["ts_ns"][-1])) == 0
+        for r in chunk:
+            assert b.advance(int(r["ts_ns"])) == 0
+            if r["target"] == 0xFFFFFFFF:
+                assert b.publish(int(r["code"]), int(r["source_id"])) == 0
+            else:
+                assert b.receive(int(r["target"]), int(r["code"]), int(r["source_id"])) == 0
+        assert b.advance(int(chunk["ts_ns"][-1])) == 0
+    for s in range(n_subs):
+        assert a.count(s) == b.count(s) and a.digest(s) == b.digest(s)
+        assert a.mailbox(s).tobytes() == b.mailbox(s).tobytes()
+    assert a.total_ticks() == b.total_ticks() > 0
+    assert [a.published_by_code(c) for c in range(17)] == [b.published_by_code(c) for c in range(17)]
+    assert a.debug_events().tobytes() == b.debug_events().tobytes()
