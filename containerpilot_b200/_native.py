@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("published_by_code", C.c_uint64 * N_CODES), ("n_subs", C.c_uint32), ("n_timers", C.c_uint32),
                 ("now_ns", C.c_uint64), ("intern_entries", C.c_uint64), ("intern_bytes", C.c_uint64),
                 ("ephemeral_live", C.c_uint64), ("ephemeral_recycled", C.c_uint64),
-                ("admit_passes", C.c_uint64), ("admit_skipped", C.c_uint64), ("admit_partial", C.c_uint64)]
+                ("admit_passes", C.c_uint64), ("admit_skipped", C.c_uint64), ("admit_partial", C.c_uint64), ("device_splits", C.c_uint64)]
 
 
 class PairCount(C.Structure):

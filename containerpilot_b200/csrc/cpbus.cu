@@ -113,6 +113,7 @@ struct cpbus {
   cpbus_event* d_drain = nullptr; size_t drain_cap = 0;        // cpbus_drain_many staging
   uint2* d_drain_idx = nullptr; size_t drain_idx_cap = 0;
   uint32_t subs_per_warp = 0;             // 0 = auto
+  uint32_t order_block = 0;               // mask order is built per block of this many consecutive subscribers (0 = one global order)
   bool pdl = true;                        // programmatic dependent launch of consecutive fan-outs
   int h2d_spin_us = 30;                   // how long cpbus_flush waits on the host for the batch's H2D before inserting a stream wait
   bool zero_copy = false;                 // fan-out pulls host-staged batches straight from pinned memory (experiment: CPBUS_ZERO_COPY=1)
@@ -227,11 +228,31 @@ void dbg_mark_device_batch(cpbus* b, unsigned long long launch) {
 }
 
 int rebuild_order(cpbus* b) {
-  std::vector<uint32_t> count((size_t)CPBUS_MASK_ALL + 2, 0);
-  for (uint32_t i = 0; i < b->n_next; i++) if (b->h_active[i]) count[(b->h_mask[i] & CPBUS_MASK_ALL) + 1]++;
-  for (size_t k = 1; k < count.size(); k++) count[k] += count[k - 1];
-  std::vector<uint32_t> order(count.back());
-  for (uint32_t i = 0; i < b->n_next; i++) if (b->h_active[i]) order[count[b->h_mask[i] & CPBUS_MASK_ALL]++] = i;
+  // Mask order: equal masks become neighbours, so a warp's consecutive mailboxes share one filter pass.  A GLOBAL order
+  // scatters the mailboxes that are written at the same time over the whole ring area (1,048,576 rings = 32 GiB = 16,384
+  // 2-MiB pages, all live at once); ordering block by block of consecutive subscribers keeps the concurrently written
+  // rings within a few hundred pages, at the price of shorter runs.
+  std::vector<uint32_t> order;
+  order.reserve(b->n_next);
+  // Same box, Zipf masks, us per launch (profiles/r02_ab_kernel_variants.md table 7): 1,048,576 subscribers (32 GiB of rings)
+  // global order 1347.5, blocks of 524,288 subscribers 1292, of 262,144 or 131,072 1279.5 (-5.0 %), of 4,096 1287;
+  // 524,288 subscribers (16 GiB): global 635.4, blocks of 262,144 643.7 (shorter runs cost 1.3 %).  Default: one global order
+  // up to 16 GiB of rings, blocks of 8 GiB beyond.  CPBUS_ORDER_BLOCK overrides (subscribers per block; -1 = global).
+  const uint64_t ring_bytes = (uint64_t)b->R * sizeof(cpbus_event);
+  uint32_t blk = b->order_block;
+  if (!blk) blk = (uint64_t)b->n_next * ring_bytes <= (16ull << 30) ? std::max(1u, b->n_next)
+                                                                    : (uint32_t)std::max<uint64_t>(4096, (8ull << 30) / ring_bytes);
+  if (b->order_block == 0xFFFFFFFFu) blk = std::max(1u, b->n_next);   // CPBUS_ORDER_BLOCK=-1: one global order (A/B)
+  std::vector<uint32_t> count((size_t)CPBUS_MASK_ALL + 2);
+  for (uint32_t lo = 0; lo < b->n_next; lo += blk) {
+    const uint32_t hi = (uint32_t)std::min<uint64_t>((uint64_t)lo + blk, b->n_next);
+    std::fill(count.begin(), count.end(), 0u);
+    for (uint32_t i = lo; i < hi; i++) if (b->h_active[i]) count[(b->h_mask[i] & CPBUS_MASK_ALL) + 1]++;
+    for (size_t k = 1; k < count.size(); k++) count[k] += count[k - 1];
+    const size_t base = order.size();
+    order.resize(base + count.back());
+    for (uint32_t i = lo; i < hi; i++) if (b->h_active[i]) order[base + count[b->h_mask[i] & CPBUS_MASK_ALL]++] = i;
+  }
   b->n_order = (uint32_t)order.size();
   if (b->n_order) {
     CK(cudaMemcpyAsync(b->d_order, order.data(), (size_t)b->n_order * 4, cudaMemcpyHostToDevice, b->stream));
@@ -565,6 +586,7 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   if (const char* e = getenv("CPBUS_ZERO_COPY")) b->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("CPBUS_HINTS")) b->hints = atoi(e);
   if (const char* e = getenv("CPBUS_SUBS_PER_WARP")) b->subs_per_warp = (uint32_t)atoi(e);   // tuning knob for experiments
+  if (const char* e = getenv("CPBUS_ORDER_BLOCK")) b->order_block = (uint32_t)atoll(e);
   int rc = CPBUS_OK;
   auto fail = [&](int code) { cpbus_destroy(b); return code; };
   if (cfg->device >= 0) b->device = cfg->device;
@@ -1028,13 +1050,54 @@ int cpbus_sync(cpbus_t* b) {
 }
 
 static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged,
+                               const void* d_next, size_t n_next);
+
+// A device batch that one launch cannot take — more than batch_cap records, or a watermark further from the last one than the
+// 32/K firings per timer slot a launch examines — is cut into slices that can (round 1 answered CPBUS_EINVAL / CPBUS_EORDER).
+// The cut needs the records' timestamps: one strided D2H of 8 bytes per record, on this slow path only.  A slice ends at
+// batch_cap records or at the window's edge, whichever comes first, and its watermark is its last record's timestamp (cut by
+// size) or the edge (cut by time): ticks due by then are merged exactly where the unsplit launch would have put them, because
+// a tick is ordered in front of every event with ts >= its due time and such events are either in this slice behind it or
+// in a later one.  The host path does the same at cpbus_advance.  (events/timer.go:40-71 has no such limit: a Go timer
+// that fell behind fires late, never "not at all".)
+static int publish_device_split(cpbus_t* b, const cpbus_event* d_events, size_t n, uint64_t watermark_ns, bool staged,
+                                const void* d_next, size_t n_next) {
+  std::vector<uint64_t> ts(n);
+  if (n) {
+    CK(cudaMemcpy2DAsync(ts.data(), 8, reinterpret_cast<const unsigned char*>(d_events) + offsetof(cpbus_event, ts_ns), sizeof(cpbus_event),
+                         8, n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (size_t i = 1; i < n; i++) if (ts[i] < ts[i - 1]) return CPBUS_EORDER;
+    if (ts[n - 1] > watermark_ns) return CPBUS_EORDER;
+  }
+  size_t i = 0;
+  for (;;) {
+    const uint64_t win = max_window(b);   // (re-read: a one-shot retiring mid-way can only widen it)
+    const uint64_t edge = (win == UINT64_MAX || watermark_ns - b->last_watermark <= win) ? watermark_ns : b->last_watermark + win;
+    size_t j = std::upper_bound(ts.begin() + i, ts.end(), edge) - ts.begin();
+    uint64_t w = edge;
+    if (j - i > b->B) { j = i + b->B; w = ts[j - 1]; }
+    const bool last = j == n && w == watermark_ns;
+    const int rc = publish_device_impl(b, d_events + i, j - i, w, staged, last ? d_next : nullptr, last ? n_next : 0);
+    if (rc) return rc;
+    b->st.device_splits++;
+    i = j;
+    if (last) return CPBUS_OK;
+  }
+}
+
+static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged,
                                const void* d_next, size_t n_next) {
-  if (!b || (!d_events && n) || n > b->B || ((uintptr_t)d_events & 31u) || n_next > b->B || ((uintptr_t)d_next & 31u)) return CPBUS_EINVAL;
+  if (!b || (!d_events && n) || ((uintptr_t)d_events & 31u) || n_next > b->B || ((uintptr_t)d_next & 31u)) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   if ((rc = flush_staged(b, b->now))) return rc;
   if (watermark_ns < b->now) return CPBUS_EORDER;
-  if (watermark_ns - b->last_watermark > max_window(b)) return CPBUS_EORDER;
   if (staged && b->lossless) return CPBUS_EINVAL;   // admission would have to read the peer batch: not supported
+  if (n > b->B || watermark_ns - b->last_watermark > max_window(b)) {
+    // lossless mode stays all-or-nothing per call (the caller owns the batch and could not tell how far a refused call got)
+    if (b->lossless) return n > b->B ? CPBUS_EINVAL : CPBUS_EORDER;
+    return publish_device_split(b, (const cpbus_event*)d_events, n, watermark_ns, staged, d_next, n_next);
+  }
   bool ok = true;
   if ((rc = admit(b, (const cpbus_event*)d_events, (uint32_t)n, watermark_ns, &ok))) return rc;
   if (!ok) return CPBUS_EAGAIN;

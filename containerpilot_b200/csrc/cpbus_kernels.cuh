@@ -42,7 +42,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define CPBUS_COLD_EARLY 1   // (+1 % on config 3 once the loop is not unrolled) cold half of the timer slot loaded before the copy loop instead of after it
 #endif
 #ifndef CPBUS_UNROLL2
-#define CPBUS_UNROLL2 0      // dense+ticks copy loop: two chunks per iteration (measured: no gain, costs registers)
+#define CPBUS_UNROLL2 1      // dense+ticks loop: two 32-event chunks per iteration (with planar staging: config 3 2647 -> 2640 us, r2v)
 #endif
 #ifndef CPBUS_EARLY_PF
 #define CPBUS_EARLY_PF 0     // (measured: neutral) prefetch.L2 of the warp's first control block / timer slot at kernel entry
@@ -53,6 +53,10 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef CPBUS_IDX_PF
 #define CPBUS_IDX_PF 1       // filtered path, pass 2: read the index list one iteration ahead (measured: -0.35 % on config 5)
 #endif
+#ifndef CPBUS_PLANAR
+#define CPBUS_PLANAR 1       // the staged batch is re-laid in shared memory as two 16-byte planes (lo[i] = bytes 0-15 of record i, hi[i] =
+#endif                       // bytes 16-31) before the copy loops: a lane's two LDS.128 are then conflict-free on the dense paths with no
+                             // select and no extra register (the lane-swapped reads of CPBUS_SWIZZLE cost registers)
 #ifndef CPBUS_ORD_RUNS
 #define CPBUS_ORD_RUNS 0     // ORDERED build: process runs of equal masks as a unit (records read once, stored to every ring of the run).
                              // Measured (profiles/r02_ab_kernel_variants.md, table 5): bit-exact, but 5.7 % SLOWER on config 5 — the rings then
@@ -279,8 +283,9 @@ __device__ __forceinline__ void st_half(void* dst, const uint4& a, bool hinted) 
 // (round 1 ncu: l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld = 0.74 per record, 44 % of stall samples short_sb).
 // Lanes 4-7 of each quarter therefore fetch their two halves in the opposite order: each wavefront then covers all 32
 // banks, and two selects per register put the halves back in place.  No re-layout of the TMA-staged batch is needed.
-template <bool GATHER = false>
-__device__ __forceinline__ void lds_record(const uint4* s4, uint32_t i, uint32_t sw, uint4& a, uint4& b) {
+template <bool GATHER = false, bool PL = false>
+__device__ __forceinline__ void lds_record(const uint4* s4, uint32_t i, uint32_t sw, uint4& a, uint4& b, uint32_t hi = 0) {
+  if (PL) { a = s4[i]; b = s4[hi + i]; return; }   // planar staging: plane lo at s4, plane hi at s4 + hi
   if (CPBUS_SWIZZLE == 0 || (CPBUS_SWIZZLE == 2 && !GATHER)) {
     a = s4[2 * i]; b = s4[2 * i + 1];
     return;
@@ -567,6 +572,33 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     mbar_wait(&s_sum->mbar_desc, 0);
     mbar_wait(&s_sum->mbar, (staged && n && !s_sum->abort_launch) ? 1u : 0u);
   }
+  // ---- planar re-layout of the staged batch (in place): record i = {lo[i], hi[i]}, lo at s4[i], hi at s4[cap + i] ----
+  // At a 32-byte lane stride the eight lanes of an LDS.128 wavefront touch only four of the eight 16-byte bank groups
+  // (2-way conflict on every record read: round 1 ncu, 0.74 conflicts per record); at a 16-byte stride they touch all
+  // eight.  All 2n chunks are read into registers (n <= 1024: at most 8 per thread), barrier, then written to their
+  // plane: two barriers and 8 shared-memory instructions per thread per CTA, against ~2000 record reads per thread.
+  // Not in the ORDERED build: its gathered reads do no better on planes than with the lane-swapped halves (same box, r2v:
+  // 1353 vs 1349 us), and not with the bulk store path, which copies whole records out of shared memory.
+  constexpr bool PLANAR = CPBUS_PLANAR && STORE != CPBUS_STORE_BULK && !ORDERED;
+  const uint32_t hi_off = cap;                                         // in 16-byte units
+  if (PLANAR && n) {
+    uint4* sq = reinterpret_cast<uint4*>(s_batch);
+    uint4 v[8];
+    __syncthreads();                       // (own_desc CTAs: every reader of the record-major batch is done)
+#pragma unroll
+    for (int r = 0; r < 8; r++) { const uint32_t q = tid + r * kThreads; if (q < 2u * n) v[r] = sq[q]; }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; r++) { const uint32_t q = tid + r * kThreads; if (q < 2u * n) sq[(q & 1u) * hi_off + (q >> 1)] = v[r]; }
+    __syncthreads();
+  }
+  // field reads from the staged batch, whichever layout it is in
+  auto ev_ts = [&](uint32_t i) -> uint64_t {
+    return PLANAR ? reinterpret_cast<const uint64_t*>(reinterpret_cast<const uint4*>(s_batch) + i)[1] : s_batch[i].ts_ns;
+  };
+  auto ev_code_src = [&](uint32_t i) -> uint2 {   // {code, source_id}
+    return PLANAR ? reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(s_batch) + hi_off + i)[0] : make_uint2(s_batch[i].code, s_batch[i].source_id);
+  };
   const bool aborted = s_sum->abort_launch != 0;   // stream batch missing: this launch delivers nothing and fires no timer
   const uint32_t K = p.K, J = K ? 32u / K : 32u;   // candidate firings per timer slot per launch (host bounds the window)
   const uint32_t tk_slot = lane / J, tk_j = lane % J;
@@ -638,8 +670,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           uint32_t i0 = o, i1 = o + 32;
           if (!dense) { i0 = v0 ? my_idx[o] : 0u; i1 = v1 ? my_idx[o + 32] : 0u; }
           uint4 a0, b0, a1, b1;
-          if (v0) lds_record<true>(s4r, i0, swr, a0, b0);
-          if (v1) lds_record<true>(s4r, i1, swr, a1, b1);
+          if (v0) lds_record<true, PLANAR>(s4r, i0, swr, a0, b0, hi_off);
+          if (v1) lds_record<true, PLANAR>(s4r, i1, swr, a1, b1, hi_off);
           if (DIGEST && !dense) {
             if (v0) acc = acc * p32 + s_rhash[i0];
             if (v1) acc = acc * p32 + s_rhash[i1];
@@ -810,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       uint32_t lo = 0, hi = n;
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (s_batch[mid].ts_ns < tk_due) lo = mid + 1; else hi = mid;
+        if (ev_ts(mid) < tk_due) lo = mid + 1; else hi = mid;
       }
       tk_pos = lo;
     }
@@ -847,12 +879,12 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       } else if (STORE == CPBUS_STORE_V8) {
         for (uint32_t i = lane; i < n; i += 32) {
           uint4 a, b;
-          lds_record(s4, i, sw, a, b);
+          lds_record<false, PLANAR>(s4, i, sw, a, b, hi_off);
           st_v8(ring + (((uint32_t)tail + i) & Rm), a, b);
         }
       } else {
         for (uint32_t q = lane; q < 2 * n; q += 32) {   // lane pair per record: 512 contiguous bytes per instruction
-          const uint4 v = s4[q];
+          const uint4 v = PLANAR ? s4[(q & 1u) * hi_off + (q >> 1)] : s4[q];
           st_v4(reinterpret_cast<unsigned char*>(ring + (((uint32_t)tail + (q >> 1)) & Rm)) + (q & 1u) * 16u, v);
         }
       }
@@ -894,8 +926,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       for (; c0 + 64 <= n; c0 += 64) {   // two chunks per iteration: both records' shared-memory loads are in flight before the selects
         const uint32_t o0 = slot_of(c0), o1 = slot_of(c0 + 32);
         uint4 a0, b0, a1, b1;
-        lds_record(s4, c0 + lane, sw, a0, b0);
-        lds_record(s4, c0 + 32 + lane, sw, a1, b1);
+        lds_record<false, PLANAR>(s4, c0 + lane, sw, a0, b0, hi_off);
+        lds_record<false, PLANAR>(s4, c0 + 32 + lane, sw, a1, b1, hi_off);
         st_record<STORE>(ring + (((uint32_t)tail + o0) & Rm), a0, b0);
         st_record<STORE>(ring + (((uint32_t)tail + o1) & Rm), a1, b1);
       }
@@ -905,7 +937,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         const uint32_t out = slot_of(c0);
         if (c0 + lane < n) {
           uint4 a, b;
-          lds_record(s4, c0 + lane, sw, a, b);
+          lds_record<false, PLANAR>(s4, c0 + lane, sw, a, b, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
         }
       }
@@ -920,7 +952,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (uint32_t t = t_idx; t < n_ticks && my_tick[t] < c0 + 32; t++) out += (my_tick[t] <= i) ? 1u : 0u;
         if (i < n) {
           uint4 a, b;
-          lds_record(s4, i, sw, a, b);
+          lds_record<false, PLANAR>(s4, i, sw, a, b, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
         }
       }
@@ -990,8 +1022,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (; o + 32 < k; o += 64) {
           const uint32_t n0 = o + 64 < k ? my_idx[o + 64] : 0u, n1 = o + 96 < k ? my_idx[o + 96] : 0u;
           uint4 a0, b0, a1, b1;
-          lds_record<ORDERED>(s4, i0, sw, a0, b0);
-          lds_record<ORDERED>(s4, i1, sw, a1, b1);
+          lds_record<ORDERED, PLANAR>(s4, i0, sw, a0, b0, hi_off);
+          lds_record<ORDERED, PLANAR>(s4, i1, sw, a1, b1, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
           st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
           if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
@@ -999,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         }
         if (o < k) {
           uint4 a, b;
-          lds_record<ORDERED>(s4, i0, sw, a, b);
+          lds_record<ORDERED, PLANAR>(s4, i0, sw, a, b, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
           if (hashing) acc = acc * p32 + s_rhash[i0];
           o += 32;
@@ -1008,8 +1040,8 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (; o + 32 < k; o += 64) {   // two outputs per lane per iteration: their index/record/hash loads are independent
           const uint32_t i0 = my_idx[o], i1 = my_idx[o + 32];
           uint4 a0, b0, a1, b1;
-          lds_record<ORDERED>(s4, i0, sw, a0, b0);
-          lds_record<ORDERED>(s4, i1, sw, a1, b1);
+          lds_record<ORDERED, PLANAR>(s4, i0, sw, a0, b0, hi_off);
+          lds_record<ORDERED, PLANAR>(s4, i1, sw, a1, b1, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a0, b0);
           st_record<STORE>(ring + (((uint32_t)tail + o + 32) & Rm), a1, b1);
           if (hashing) acc = (acc * p32 + s_rhash[i0]) * p32 + s_rhash[i1];
@@ -1017,7 +1049,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         for (; o < k; o += 32) {
           const uint32_t i = my_idx[o];
           uint4 a, b;
-          lds_record<ORDERED>(s4, i, sw, a, b);
+          lds_record<ORDERED, PLANAR>(s4, i, sw, a, b, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + o) & Rm), a, b);
           if (hashing) acc = acc * p32 + s_rhash[i];
         }
@@ -1047,7 +1079,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           if (match) {
             const uint32_t out = base + __popc(w & ((1u << lane) - 1u));
             uint4 a, b;
-            lds_record(s4, i, sw, a, b);
+            lds_record<false, PLANAR>(s4, i, sw, a, b, hi_off);
             st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
             if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
           }
@@ -1077,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
         }
         if (PAIRS && n_pairs && __any_sync(0xffffffffu, cand)) {
           uint32_t ev_code = kPairNone - 1u, ev_src = 0;          // never equals a pair
-          if (cand) { ev_code = s_batch[i].code; ev_src = s_batch[i].source_id; }
+          if (cand) { const uint2 cs = ev_code_src(i); ev_code = cs.x; ev_src = cs.y; }
           for (uint32_t j = 0; j < n_pairs; j++) {
             const uint32_t pc = __shfl_sync(0xffffffffu, my_pair.x, j), ps = __shfl_sync(0xffffffffu, my_pair.y, j);
             match = match || (ev_code == pc && ev_src == ps);
@@ -1113,7 +1145,7 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
           uint32_t out = mrank;
           for (uint32_t t = 0; t < n_ticks; t++) out += (my_tick[t] <= mrank) ? 1u : 0u;
           uint4 a, b;
-          lds_record(s4, i, sw, a, b);
+          lds_record<false, PLANAR>(s4, i, sw, a, b, hi_off);
           st_record<STORE>(ring + (((uint32_t)tail + out) & Rm), a, b);
           if (DIGEST) dsum += s_rhash[i] * s_pow[k - 1 - out];
         }
@@ -1186,10 +1218,11 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
     if (tid < 32 && tid != CPBUS_METRIC && s_dsum[2 + tid]) atomicAdd(&p.acct->by_code[tid], (unsigned long long)s_dsum[2 + tid]);
     for (uint32_t i = tid; i < n; i += kThreads) {
       if (s_meta[i].y != CPBUS_TARGET_ALL) continue;
-      const uint32_t code = s_batch[i].code;
+      const uint2 cs = ev_code_src(i);
+      const uint32_t code = cs.x;
       if (code == CPBUS_METRIC || code >= 32u) continue;
-      const unsigned long long key = (((unsigned long long)code << 32) | s_batch[i].source_id) + 1ull;
-      uint32_t slot = pair_key_hash(code, s_batch[i].source_id) & (kAcctPairSlots - 1u);
+      const unsigned long long key = (((unsigned long long)code << 32) | cs.y) + 1ull;
+      uint32_t slot = pair_key_hash(code, cs.y) & (kAcctPairSlots - 1u);
       bool placed = false;
       for (int probe = 0; probe < 32 && !placed; probe++, slot = (slot + 1u) & (kAcctPairSlots - 1u)) {
         const unsigned long long old = atomicCAS(&p.acct->pair_key[slot], 0ull, key);
@@ -1204,7 +1237,13 @@ __global__ void __launch_bounds__(kThreads, CPBUS_CTAS_PER_SM) fanout_kernel(con
       for (uint32_t c = 0; c < 32; c++) nb += s_dsum[2 + c];
       for (uint32_t i = n; i > 0 && kept < (uint32_t)kAcctDbgKeep; i--)
         if (s_meta[i - 1].y == CPBUS_TARGET_ALL) idx[kept++] = i - 1;
-      for (uint32_t j = 0; j < kept; j++) t->ev[j] = s_batch[idx[kept - 1 - j]];
+      for (uint32_t j = 0; j < kept; j++) {
+        const uint32_t i = idx[kept - 1 - j];
+        if (PLANAR) {
+          uint4* o = reinterpret_cast<uint4*>(&t->ev[j]);
+          o[0] = reinterpret_cast<const uint4*>(s_batch)[i]; o[1] = reinterpret_cast<const uint4*>(s_batch)[hi_off + i];
+        } else t->ev[j] = s_batch[i];
+      }
       t->n_broadcast = nb; t->n_kept = kept;
       __threadfence();
       t->launch_seq = p.launch_seq;

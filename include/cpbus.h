@@ -136,6 +136,7 @@ typedef struct cpbus_stats_t {
   uint64_t admit_passes;   /* lossless mode: flushes that needed the admission kernel (+ one host sync) ... */
   uint64_t admit_skipped;  /* ... and flushes that provably fitted and went straight to the fan-out        */
   uint64_t admit_partial;  /* flushes that delivered only the prefix every mailbox could take (then EAGAIN)  */
+  uint64_t device_splits;  /* slices launched for device batches one launch could not take (see cpbus_publish_device) */
 } cpbus_stats_t;
 
 typedef struct cpbus cpbus_t;
@@ -212,8 +213,12 @@ int cpbus_flush(cpbus_t* bus);
 int cpbus_sync(cpbus_t* bus);
 /* Fan out a batch that is already resident in HBM (multi-GPU: the NCCL-broadcast
  * stream; bench: device-resident trace).  Records are complete
- * (seq/ts/target/flags set by the producer), sorted by ts_ns, n <= batch_cap,
- * 32-byte aligned.  watermark_ns >= last ts; becomes the bus clock. */
+ * (seq/ts/target/flags set by the producer), sorted by ts_ns, 32-byte aligned.
+ * watermark_ns >= last ts; becomes the bus clock.  One launch takes up to batch_cap
+ * records and a watermark step of up to 32/timers_per_sub periods of the fastest armed
+ * timer; a batch beyond either is cut into several launches (the cut reads the records'
+ * timestamps back, 8 bytes each: a slow path, counted in cpbus_stats.device_splits).
+ * Lossless mode keeps the strict form: CPBUS_EINVAL / CPBUS_EORDER for such a batch. */
 int cpbus_publish_device(cpbus_t* bus, const void* d_events, size_t n, uint64_t watermark_ns);
 /* (Batches published this way are accounted for by the kernel itself: cpbus_stats.published_by_code,
  * cpbus_publish_counts and cpbus_debug_events see their broadcast events exactly as if they had gone through cpbus_publish.) */

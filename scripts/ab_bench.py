@@ -68,4 +68,4 @@ if __name__ == "__main__":
             if "config3" in which:
                 run(os.path.abspath(lib), "config3", 1_048_576, 1, None)
             if "config5" in which:
-                run(os.path.abspath(lib), "config5", 1_048_576, 0, 1.0)
+                run(os.path.abspath(lib), "config5", int(os.environ.get("AB_SUBS5", "1048576")), 0, 1.0)

@@ -112,10 +112,14 @@ def test_timer_heavy_config3_shape():
         assert st["ticks"] == n_subs * (n_events * dt // 1_000_000)
 
 
-def test_zipf_filter_sweep_scaled():
-    """BASELINE config 5 shape, scaled: Zipf-skewed masks and event codes."""
+@pytest.mark.parametrize("order_block", [None, "64", "1000", "-1"])
+def test_zipf_filter_sweep_scaled(order_block, monkeypatch):
+    """BASELINE config 5 shape, scaled: Zipf-skewed masks and event codes.  The mask order is built per block of consecutive
+    subscribers (locality of the rings written at the same time); CPBUS_ORDER_BLOCK forces small blocks / one global order."""
+    if order_block is not None:
+        monkeypatch.setenv("CPBUS_ORDER_BLOCK", order_block)
     n_subs, n_events = 2048, 8000
-    for s_exp in (0.5, 1.0, 1.5):
+    for s_exp in ((0.5, 1.0, 1.5) if order_block is None else (1.0,)):
         masks = tr.zipf_masks(n_subs, s_exp, 21); codes = tr.zipf_codes(n_events, s_exp, 22)
         srcs = (np.arange(n_events) % 4096).astype(np.uint32)
         orc = ob.Oracle(n_subs, keep_window=1024)
@@ -409,6 +413,65 @@ def test_large_clock_jump_is_split_into_bounded_windows():
             nat.check(bus.flush(), "flush"); bus.sync()
             st = tr.compare(bus, orc, 6, window=2048)
             assert st["ticks"] > 1500
+
+
+@pytest.mark.parametrize("K,period,staged", [(0, 0, False), (1, 900, False), (4, 700, False), (2, 1100, True)])
+def test_oversize_device_batches_are_split(K, period, staged):
+    """cpbus_publish_device with more records than batch_cap and a watermark step of hundreds of timer periods (round 1:
+    CPBUS_EINVAL / CPBUS_EORDER): the library cuts the batch by size and by timer window; mailboxes equal the oracle's, which
+    takes the same records event by event.  Timestamps repeat, and some coincide with due times (tick goes in front)."""
+    import torch
+    n_subs, B = 40, 256
+    rng = np.random.default_rng(1234 + K)
+    masks = np.where(rng.random(n_subs) < 0.5, nat.MASK_ALL, rng.integers(1, 1 << 17, n_subs)).astype(np.uint32)
+    orc = ob.Oracle(n_subs, timers_per_sub=K, keep_window=8192)
+    with Bus(n_subs, ring_cap=8192, batch_cap=B, timers_per_sub=K, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        for s, m in enumerate(masks):
+            orc.subscribe(int(m)); bus.subscribe(int(m))
+            for j in range(K):
+                per = period + 13 * s + 101 * j
+                orc.timer_add(s, per, 900 + 8 * s + j, j == 3); bus.timer_add(s, per, 900 + 8 * s + j, j == 3)
+        seq, now, splits = 0, 0, 0
+        for n, span in ((1500, 40_000), (0, 90_000), (700, 0), (300, 500), (B + 1, 1), (B, 30_000)):
+            ts = np.sort(rng.integers(now, now + span + 1, n)).astype(np.uint64)
+            if n > 8 and K:
+                ts[n // 3] = ts[n // 3 + 1] = ((ts[n // 3] // period) + 1) * period      # an event exactly at a due time, twice
+                ts = np.sort(np.minimum(ts, now + span))
+            ev = np.zeros(n, dtype=EVENT_DTYPE)
+            ev["seq"] = seq + np.arange(n); ev["ts_ns"] = ts
+            ev["code"] = rng.integers(0, 17, n); ev["source_id"] = rng.integers(0, 50, n); ev["target"] = nat.TARGET_ALL
+            seq += n; now += span
+            assert orc.publish_records(ev, now) == 0
+            dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32).copy()).cuda() if n else None
+            ptr = dev.data_ptr() if n else 0
+            if staged:
+                nat.check(bus.publish_device_staged(ptr, n, now, 0, 0), "cpbus_publish_device_staged")
+            else:
+                nat.check(bus.publish_device(ptr, n, now), "cpbus_publish_device")
+            bus.sync()
+        st = tr.compare(bus, orc, n_subs, window=8192)
+        assert st["device_splits"] >= (1500 + B - 1) // B + 3 + 2 + 2
+        if K:
+            assert st["ticks"] > 1000
+        # unsorted or beyond the watermark: refused before anything is launched
+        bad = np.zeros(2 * B + 16, dtype=EVENT_DTYPE); bad["ts_ns"] = now + 10; bad["ts_ns"][7] = now + 5; bad["target"] = nat.TARGET_ALL
+        d = torch.from_numpy(bad.view(np.uint8).reshape(-1, 32).copy()).cuda()
+        before = bus.stats()["kernel_launches"]
+        assert bus.publish_device(d.data_ptr(), 2 * B + 16, now + 10) == nat.EORDER
+        assert bus.publish_device(d.data_ptr() + 8 * 32, 2 * B + 8, now + 9) == nat.EORDER
+        assert bus.stats()["kernel_launches"] == before
+
+
+def test_oversize_device_batch_in_lossless_mode_is_refused():
+    import torch
+    with Bus(4, ring_cap=1024, batch_cap=64, lossless=True, stream=torch.cuda.current_stream().cuda_stream) as bus:
+        bus.subscribe()
+        ev = np.zeros(65, dtype=EVENT_DTYPE); ev["target"] = nat.TARGET_ALL; ev["code"] = 3
+        d = torch.from_numpy(ev.view(np.uint8).reshape(-1, 32).copy()).cuda()
+        assert bus.publish_device(d.data_ptr(), 65, 0) == nat.EINVAL
+        nat.check(bus.publish_device(d.data_ptr(), 64, 0), "cpbus_publish_device")
+        bus.sync()
+        assert len(bus.drain(0)) == 64
 
 
 @pytest.mark.parametrize("seed", range(100, 116))
