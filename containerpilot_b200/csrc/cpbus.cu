@@ -344,7 +344,10 @@ int launch_fanout(cpbus* b, const cpbus_event* d_src, uint32_t n, uint64_t w, in
     if (b->order_dirty) { const int rc_order = rebuild_order(b); if (rc_order) return rc_order; }
     if (b->n_order) {
       const uint32_t scale = std::max(1u, (p.n_ev + 128u) / 256u);
-      uint32_t spw = b->subs_per_warp ? std::min(32u, b->subs_per_warp) : std::max(4u, 16u / scale);   // measured: 8 at 512-event batches
+      // measured at 512-event batches: 8 mailboxes per warp from 524,288 subscribers up, 6 at 262,144 (-0.7 %), 4 at 131,072
+      // (-2.8 %: short launches want more, shorter CTAs) — gpurun_out/r2y_ab.txt
+      uint32_t spw = b->subs_per_warp ? std::min(32u, b->subs_per_warp)
+                                      : std::max(4u, std::min(16u / scale, b->n_order / (20480u * scale)));
       p.order = b->d_order; p.n_order = b->n_order; p.spw = spw;
       const uint32_t warps = (b->n_order + spw - 1) / spw;
       grid = std::max(1u, (warps + kWarpsPerCta - 1) / kWarpsPerCta);
