@@ -11,6 +11,8 @@ timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_s
   -k 'shards_match and (1-0-0 or 2-1-3) or descriptor_itself' > gpurun_out/${T}_racecheck_stream.txt 2>&1; tail -n 4 gpurun_out/${T}_racecheck_stream.txt
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider \
   -k 'config1 or random_mixed_traces and (1-1 or 2-4) or timer_heavy or zipf' > gpurun_out/${T}_memcheck_parity.txt 2>&1; tail -n 4 gpurun_out/${T}_memcheck_parity.txt
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider \
+  -k 'config1 or timer_heavy or zipf_filter_sweep_scaled and 64 or oversize' > gpurun_out/${T}_racecheck_parity.txt 2>&1; tail -n 4 gpurun_out/${T}_racecheck_parity.txt
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
 timeout 900 python bench.py --gpus 1 --steps 2000 --warmup 5 --no-cpu > gpurun_out/${T}_bench2000.json 2> gpurun_out/${T}_bench2000.err; echo "bench2000 rc=$?"
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${T}_ref.json 2> gpurun_out/${T}_ref.err; echo "ref rc=$?"
