@@ -228,45 +228,52 @@ void dbg_mark_device_batch(cpbus* b, unsigned long long launch) {
   if (b->dbg_pending.size() > (size_t)kAcctDbgRing) b->dbg_pending.pop_front();
 }
 
-int rebuild_order(cpbus* b) {
-  // Mask order: equal masks become neighbours, so a warp's consecutive mailboxes share one filter pass.  A GLOBAL order
-  // scatters the mailboxes that are written at the same time over the whole ring area (1,048,576 rings = 32 GiB = 16,384
-  // 2-MiB pages, all live at once); ordering block by block of consecutive subscribers keeps the concurrently written
-  // rings within a few hundred pages, at the price of shorter runs.
-  std::vector<uint32_t> order;
-  order.reserve(b->n_next);
-  // Same box, Zipf masks, us per launch (profiles/r02_ab_kernel_variants.md table 7): 1,048,576 subscribers (32 GiB of rings)
-  // global order 1347.5, blocks of 524,288 subscribers 1292, of 262,144 or 131,072 1279.5 (-5.0 %), of 4,096 1287;
-  // 524,288 subscribers (16 GiB): global 635.4, blocks of 262,144 643.7 (shorter runs cost 1.3 %).  Default: one global order
-  // up to 16 GiB of rings, blocks of 8 GiB beyond.  CPBUS_ORDER_BLOCK overrides (subscribers per block; -1 = global).
-  const uint64_t ring_bytes = (uint64_t)b->R * sizeof(cpbus_event);
-  uint32_t blk = b->order_block;
-  if (!blk) blk = (uint64_t)b->n_next * ring_bytes <= (16ull << 30) ? std::max(1u, b->n_next)
-                                                                    : (uint32_t)std::max<uint64_t>(4096, (8ull << 30) / ring_bytes);
-  if (b->order_block == 0xFFFFFFFFu) blk = std::max(1u, b->n_next);   // CPBUS_ORDER_BLOCK=-1: one global order (A/B)
+// The mask order of the ORDERED build, host-only (exported as cpbus_mask_order so that it can be tested without a GPU).
+// Equal masks become neighbours, so a warp's consecutive mailboxes share one filter pass.
+//  * Blocks.  A GLOBAL order scatters the mailboxes that are written at the same time over the whole ring area (1,048,576
+//    rings = 32 GiB = 16,384 2-MiB pages, all live at once); ordering block by block of consecutive subscribers keeps the
+//    concurrently written rings within a few hundred pages, at the price of shorter runs.  Same box, Zipf masks, us per launch
+//    (profiles/r02_ab_kernel_variants.md table 8): 1,048,576 subscribers (32 GiB of rings) global order 1347.5, blocks of
+//    524,288 subscribers 1292, of 262,144 or 131,072 1279.5 (-5.0 %), of 4,096 1287; 524,288 subscribers (16 GiB): global
+//    635.4, blocks of 262,144 643.7 (shorter runs cost 1.3 %).  Policy (block == 0): one global order up to 16 GiB of rings,
+//    blocks of 8 GiB beyond.
+//  * Heavy first.  Within a block a second, stable pass by the number of codes in the mask, most first: CTAs are dispatched
+//    in block order, so the mailboxes that take the most records start first and the launch's last wave is made of the light
+//    ones (shorter tail before the next launch may start); equal masks stay neighbours.  Table 9: 131,072 subscribers
+//    167.2 -> 162.0 us per launch, 262,144 319.5 -> 309.2, 1,048,576 1279.4 -> 1274.6.
+static void mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block, bool heavy_first,
+                       std::vector<uint32_t>& order) {
+  order.clear();
+  order.reserve(n);
+  const uint64_t ring_bytes = (uint64_t)ring_cap * sizeof(cpbus_event);
+  uint32_t blk = block;
+  if (!blk) blk = (uint64_t)n * ring_bytes <= (16ull << 30) ? std::max(1u, n) : (uint32_t)std::max<uint64_t>(4096, (8ull << 30) / ring_bytes);
+  if (block == 0xFFFFFFFFu) blk = std::max(1u, n);   // one global order (A/B)
   std::vector<uint32_t> count((size_t)CPBUS_MASK_ALL + 2), tmp;
-  for (uint32_t lo = 0; lo < b->n_next; lo += blk) {
-    const uint32_t hi = (uint32_t)std::min<uint64_t>((uint64_t)lo + blk, b->n_next);
+  for (uint32_t lo = 0; lo < n; lo += blk) {
+    const uint32_t hi = (uint32_t)std::min<uint64_t>((uint64_t)lo + blk, n);
     std::fill(count.begin(), count.end(), 0u);
-    for (uint32_t i = lo; i < hi; i++) if (b->h_active[i]) count[(b->h_mask[i] & CPBUS_MASK_ALL) + 1]++;
+    for (uint32_t i = lo; i < hi; i++) if (!active || active[i]) count[(masks[i] & CPBUS_MASK_ALL) + 1]++;
     for (size_t k = 1; k < count.size(); k++) count[k] += count[k - 1];
     const size_t base = order.size();
     order.resize(base + count.back());
-    for (uint32_t i = lo; i < hi; i++) if (b->h_active[i]) order[base + count[b->h_mask[i] & CPBUS_MASK_ALL]++] = i;
-    if (b->order_heavy_first) {
-      // second (stable) pass by the number of codes in the mask, most first: CTAs are dispatched in block order, so the mailboxes
-      // that take the most records start first and the launch's last wave is made of the light ones (shorter tail before the
-      // next launch may start); equal masks stay neighbours.  Same box, Zipf masks (gpurun_out/r3c_ab.txt): 131,072 subscribers
-      // 167.2 -> 162.0 us per launch, 262,144 319.5 -> 309.2, 1,048,576 1279.4 -> 1274.6.
+    for (uint32_t i = lo; i < hi; i++) if (!active || active[i]) order[base + count[masks[i] & CPBUS_MASK_ALL]++] = i;
+    if (heavy_first) {
       const size_t nb = order.size() - base;
       uint32_t pc_count[34] = {};
-      for (size_t k = 0; k < nb; k++) pc_count[32 - __builtin_popcount(b->h_mask[order[base + k]] & CPBUS_MASK_ALL) + 1]++;
+      for (size_t k = 0; k < nb; k++) pc_count[32 - __builtin_popcount(masks[order[base + k]] & CPBUS_MASK_ALL) + 1]++;
       for (int k = 1; k < 34; k++) pc_count[k] += pc_count[k - 1];
       tmp.resize(nb);
-      for (size_t k = 0; k < nb; k++) tmp[pc_count[32 - __builtin_popcount(b->h_mask[order[base + k]] & CPBUS_MASK_ALL)]++] = order[base + k];
+      for (size_t k = 0; k < nb; k++) tmp[pc_count[32 - __builtin_popcount(masks[order[base + k]] & CPBUS_MASK_ALL)]++] = order[base + k];
       std::copy(tmp.begin(), tmp.end(), order.begin() + base);
     }
   }
+}
+
+int rebuild_order(cpbus* b) {
+  std::vector<uint32_t> order;
+  static_assert(sizeof(b->h_active[0]) == 1, "h_active is a byte vector");
+  mask_order(b->h_mask.data(), reinterpret_cast<const uint8_t*>(b->h_active.data()), b->n_next, b->R, b->order_block, b->order_heavy_first, order);
   b->n_order = (uint32_t)order.size();
   if (b->n_order) {
     CK(cudaMemcpyAsync(b->d_order, order.data(), (size_t)b->n_order * 4, cudaMemcpyHostToDevice, b->stream));
@@ -527,6 +534,13 @@ bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 extern "C" {
 
 uint32_t cpbus_abi_version(void) { return 2; }
+size_t cpbus_mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block, int heavy_first, uint32_t* out) {
+  if (!masks || !out || !ring_cap) return 0;
+  std::vector<uint32_t> order;
+  mask_order(masks, active, n, ring_cap, block, heavy_first != 0, order);
+  std::copy(order.begin(), order.end(), out);
+  return order.size();
+}
 
 const char* cpbus_last_cuda_error(void) { return g_cuda_err; }
 

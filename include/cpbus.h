@@ -346,6 +346,13 @@ uint32_t cpbus_abi_version(void);
  * oracle and external checkers can reproduce it without reading kernel code) */
 uint64_t cpbus_record_hash(const cpbus_event* ev);
 uint64_t cpbus_digest_multiplier(void);
+/* The order in which the filtered (ORDERED) fan-out walks the mailboxes, as a pure host function (no device needed):
+ * out[] receives the indices i < n with active[i] != 0 (active == NULL: all), grouped per block of `block` consecutive
+ * subscribers (0 = the library's policy from n and ring_cap: one block up to 16 GiB of rings, 8-GiB blocks beyond;
+ * 0xFFFFFFFF = one block), inside a block by code mask — equal masks adjacent — and, with heavy_first, masks with more
+ * codes first.  Returns the number of indices written.  Delivery results never depend on this order. */
+size_t cpbus_mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block,
+                        int heavy_first, uint32_t* out);
 
 #ifdef __cplusplus
 }

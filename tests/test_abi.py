@@ -124,3 +124,47 @@ def test_header_is_plain_c99_and_a_c_caller_links():
     if not torch.cuda.is_available():            # without a device the program must stop at cpbus_create with ENODEV, loudly
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 1 and "no CUDA device" in r.stdout
+
+
+def _mask_order(masks, active, ring_cap, block, heavy):
+    lib = nat.load()
+    masks = np.ascontiguousarray(masks, dtype=np.uint32)
+    act = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
+    out = np.zeros(len(masks), dtype=np.uint32)
+    k = lib.cpbus_mask_order(masks.ctypes.data, act.ctypes.data if act is not None else None, len(masks), ring_cap, block, int(heavy), out.ctypes.data)
+    return out[:k]
+
+
+def test_mask_order_host_logic():
+    """The walk order of the filtered fan-out (host-only): a permutation of the active subscribers, block by block of
+    consecutive ids, equal masks adjacent inside a block, masks with more codes first when asked."""
+    import trace as tr
+    n = 20_000
+    masks = tr.zipf_masks(n, 1.0, 5)
+    active = (np.random.default_rng(9).random(n) < 0.9).astype(np.uint8)
+    for block, heavy in ((0, False), (0, True), (0xFFFFFFFF, True), (4096, False), (4096, True), (1000, True)):
+        o = _mask_order(masks, active, 1024, block, heavy)
+        assert sorted(o.tolist()) == np.flatnonzero(active).tolist()                 # exactly the active ones, once each
+        blk = n if block in (0, 0xFFFFFFFF) else block                                # 20,000 x 32 KiB < 16 GiB: policy = one block
+        bid = o // blk
+        assert (np.diff(bid.astype(np.int64)) >= 0).all()                             # blocks in id order
+        for b in np.unique(bid):
+            m = masks[o[bid == b]] & 0x1FFFF
+            runs = np.flatnonzero(np.diff(m.astype(np.int64)) != 0).size + 1
+            assert runs == np.unique(m).size                                          # every mask is ONE run inside the block
+            if heavy:
+                pc = np.array([bin(int(x)).count("1") for x in m])
+                assert (np.diff(pc) <= 0).all()                                       # more codes first
+            else:
+                assert (np.diff(m.astype(np.int64)) >= 0).all()                       # plain mask order
+            ids = o[bid == b]
+            for mv in np.unique(m)[:20]:
+                assert (np.diff(ids[m == mv].astype(np.int64)) > 0).all()             # stable: ids ascending inside a run
+    # the footprint policy: 1,048,576 rings of 32 KiB = 32 GiB -> blocks of 8 GiB = 262,144 subscribers
+    big = np.full(1 << 20, 0x1FFFF, dtype=np.uint32); big[1::2] = 0x2
+    o = _mask_order(big, None, 1024, 0, True)
+    assert len(o) == 1 << 20
+    first = o[: 1 << 18]
+    assert first.max() < (1 << 18) and (first[: 1 << 17] % 2 == 0).all() and (first[1 << 17:] % 2 == 1).all()
+    o2 = _mask_order(big[: 1 << 19], None, 1024, 0, True)                            # 16 GiB: one global block
+    assert (o2[: 1 << 18] % 2 == 0).all()
