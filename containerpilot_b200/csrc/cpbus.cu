@@ -532,14 +532,20 @@ bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
 }  // namespace
 
 extern "C" {
+// Nothing may unwind through the C boundary (cgo, ctypes): every status-returning entry point is a function-try-block.
+#define CPBUS_CATCH                                                                                   \
+  catch (const std::bad_alloc&) { return CPBUS_ENOMEM; }                                              \
+  catch (...) { snprintf(g_cuda_err, sizeof(g_cuda_err), "unexpected C++ exception"); return CPBUS_ECUDA; }
 
 uint32_t cpbus_abi_version(void) { return 2; }
 size_t cpbus_mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block, int heavy_first, uint32_t* out) {
   if (!masks || !out || !ring_cap) return 0;
-  std::vector<uint32_t> order;
-  mask_order(masks, active, n, ring_cap, block, heavy_first != 0, order);
-  std::copy(order.begin(), order.end(), out);
-  return order.size();
+  try {
+    std::vector<uint32_t> order;
+    mask_order(masks, active, n, ring_cap, block, heavy_first != 0, order);
+    std::copy(order.begin(), order.end(), out);
+    return order.size();
+  } catch (const std::bad_alloc&) { return 0; }
 }
 
 const char* cpbus_last_cuda_error(void) { return g_cuda_err; }
@@ -570,7 +576,7 @@ const char* cpbus_code_name(int code) {
 }
 
 // FromString — events/events.go:52-86
-int cpbus_code_from_string(const char* name) {
+int cpbus_code_from_string(const char* name) try {
   if (!name) return -1;
   static const std::unordered_map<std::string, int> table = {
       {"exitSuccess", CPBUS_EXIT_SUCCESS}, {"exitFailed", CPBUS_EXIT_FAILED}, {"stopping", CPBUS_STOPPING},
@@ -581,7 +587,7 @@ int cpbus_code_from_string(const char* name) {
       {"SIGHUP", CPBUS_SIGNAL}, {"SIGUSR2", CPBUS_SIGNAL}};
   auto it = table.find(name);
   return it == table.end() ? -1 : it->second;
-}
+} CPBUS_CATCH
 
 uint64_t cpbus_record_hash(const cpbus_event* e) {
   return record_hash_words(e->seq, e->ts_ns, (uint64_t)e->code | ((uint64_t)e->source_id << 32),
@@ -589,7 +595,7 @@ uint64_t cpbus_record_hash(const cpbus_event* e) {
 }
 uint64_t cpbus_digest_multiplier(void) { return kDigestP; }
 
-int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
+int cpbus_create(const cpbus_config* cfg, cpbus_t** out) try {
   if (!cfg || !out) return CPBUS_EINVAL;
   *out = nullptr;
   const uint32_t R = cfg->ring_cap ? cfg->ring_cap : 1024;
@@ -694,9 +700,9 @@ int cpbus_create(const cpbus_config* cfg, cpbus_t** out) {
   b->sources.emplace_back();
   *out = b;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_destroy(cpbus_t* b) {
+int cpbus_destroy(cpbus_t* b) try {
   if (!b) return CPBUS_EINVAL;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
@@ -729,9 +735,9 @@ int cpbus_destroy(cpbus_t* b) {
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_intern(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
+int cpbus_intern(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) try {
   if (!b || (!s && len) || !source_id) return CPBUS_EINVAL;
   std::string key(s ? s : "", len);
   auto it = b->intern.find(key);
@@ -744,11 +750,11 @@ int cpbus_intern(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
   b->intern.emplace(std::move(key), id);
   *source_id = id;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Bounded region for payload strings (control/endpoints.go:125-126: Source = "key|value" of every posted metric).
 // id = EPHEMERAL_BIT | generation(15) << 16 | slot(16); the slot's previous string is dropped when it is reused.
-int cpbus_intern_ephemeral(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) {
+int cpbus_intern_ephemeral(cpbus_t* b, const char* s, size_t len, uint32_t* source_id) try {
   if (!b || (!s && len) || !source_id) return CPBUS_EINVAL;
   std::string key(s ? s : "", len);
   auto perm = b->intern.find(key);
@@ -768,9 +774,9 @@ int cpbus_intern_ephemeral(cpbus_t* b, const char* s, size_t len, uint32_t* sour
   b->eph_map.emplace(std::move(key), slot);
   *source_id = CPBUS_EPHEMERAL_BIT | ((e.gen & 0x7FFFu) << 16) | slot;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_source(cpbus_t* b, uint32_t id, char* out, size_t cap, size_t* len) {
+int cpbus_source(cpbus_t* b, uint32_t id, char* out, size_t cap, size_t* len) try {
   if (!b) return CPBUS_EINVAL;
   if (id & CPBUS_EPHEMERAL_BIT) {
     const uint32_t slot = id & 0xFFFFu, gen = (id >> 16) & 0x7FFFu;
@@ -785,9 +791,9 @@ int cpbus_source(cpbus_t* b, uint32_t id, char* out, size_t cap, size_t* len) {
   if (len) *len = s.size();
   if (out && cap) memcpy(out, s.data(), std::min(cap, s.size()));
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t* first_sub_id) {
+int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t* first_sub_id) try {
   if (!b || !n) return CPBUS_EINVAL;
   if ((uint64_t)b->n_next + n > b->N) return CPBUS_ENOSPC;
   int rc = dev_guard(b); if (rc) return rc;
@@ -806,13 +812,13 @@ int cpbus_subscribe_many(cpbus_t* b, const uint32_t* masks, uint32_t n, uint32_t
   b->n_next += n; b->n_active += n; b->order_dirty = true;
   if (first_sub_id) *first_sub_id = b->cfg.sub_id_base + first;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 int cpbus_subscribe(cpbus_t* b, uint32_t mask, uint32_t* sub_id) { return cpbus_subscribe_many(b, &mask, 1, sub_id); }
 
 static int push_mask_words(cpbus* b, uint32_t first, uint32_t n);
 
-int cpbus_subscribe_pairs(cpbus_t* b, uint32_t mask, const cpbus_pair* pairs, uint32_t n_pairs, uint32_t* sub_id) {
+int cpbus_subscribe_pairs(cpbus_t* b, uint32_t mask, const cpbus_pair* pairs, uint32_t n_pairs, uint32_t* sub_id) try {
   if (!b || n_pairs > CPBUS_MAX_PAIRS || (n_pairs && !pairs)) return CPBUS_EINVAL;
   for (uint32_t j = 0; j < n_pairs; j++) if (pairs[j].code >= CPBUS_N_CODES) return CPBUS_EINVAL;
   // a pair whose code is already in the mask adds nothing; what is left decides whether a table is needed at all
@@ -840,10 +846,10 @@ int cpbus_subscribe_pairs(cpbus_t* b, uint32_t mask, const cpbus_pair* pairs, ui
   if ((rc = push_mask_words(b, l, 1))) return rc;
   if (sub_id) *sub_id = id;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 int cpbus_subscribe_pairs_many(cpbus_t* b, const uint32_t* masks, const cpbus_pair* pairs, const uint32_t* n_pairs,
-                               uint32_t n, uint32_t* first_sub_id) {
+                               uint32_t n, uint32_t* first_sub_id) try {
   if (!b || !n || !masks || !pairs || !n_pairs) return CPBUS_EINVAL;
   for (uint32_t i = 0; i < n; i++) {
     if (n_pairs[i] > CPBUS_MAX_PAIRS) return CPBUS_EINVAL;
@@ -880,9 +886,9 @@ int cpbus_subscribe_pairs_many(cpbus_t* b, const uint32_t* masks, const cpbus_pa
   if (paired && (rc = push_mask_words(b, l0, n))) return rc;
   if (first_sub_id) *first_sub_id = first;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
+int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) try {
   if (!b) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
@@ -906,12 +912,12 @@ int cpbus_unsubscribe(cpbus_t* b, uint32_t sub_id) {
   CK(cudaStreamSynchronize(b->stream));
   b->n_active--;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Change a subscriber's code mask in place (ordered with publishes like Subscribe): the subscriber keeps its mailbox,
 // its timers and its exact cases.  Used when a mailbox that so far only received timer ticks / direct sends (mask 0:
 // NewEventTimer on a channel that was not subscribed, watches/watches.go:37,71) is subscribed to the bus after all.
-int cpbus_set_mask(cpbus_t* b, uint32_t sub_id, uint32_t mask) {
+int cpbus_set_mask(cpbus_t* b, uint32_t sub_id, uint32_t mask) try {
   if (!b) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
@@ -923,7 +929,7 @@ int cpbus_set_mask(cpbus_t* b, uint32_t sub_id, uint32_t mask) {
   if (mask != CPBUS_MASK_ALL) b->n_filtered++;
   b->h_mask[l] = mask; b->order_dirty = true;
   return push_mask_words(b, l, 1);
-}
+} CPBUS_CATCH
 
 static int push_mask_words(cpbus* b, uint32_t first, uint32_t n) {
   std::vector<uint32_t> words(n);
@@ -933,7 +939,7 @@ static int push_mask_words(cpbus* b, uint32_t first, uint32_t n) {
   return CPBUS_OK;
 }
 
-int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id) {
+int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t source_id, int oneshot, uint32_t* timer_id) try {
   if (!b || !period_ns) return CPBUS_EINVAL;
   if (!b->K) return CPBUS_ENOSPC;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
@@ -958,10 +964,10 @@ int cpbus_timer_add(cpbus_t* b, uint32_t sub_id, uint64_t period_ns, uint32_t so
     return push_mask_words(b, l, 1);
   }
   return CPBUS_ENOSPC;
-}
+} CPBUS_CATCH
 
 int cpbus_timer_add_many(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t period_ns, const uint32_t* source_ids,
-                         uint32_t source_id0, int oneshot) {
+                         uint32_t source_id0, int oneshot) try {
   if (!b || !period_ns || !n) return CPBUS_EINVAL;
   if (!b->K) return CPBUS_ENOSPC;
   const uint32_t l0 = first_sub - b->cfg.sub_id_base;
@@ -992,9 +998,9 @@ int cpbus_timer_add_many(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t pe
   b->n_timers += n;
   if (!oneshot) b->min_period = std::min(b->min_period, period_ns);
   return push_mask_words(b, l0, n);
-}
+} CPBUS_CATCH
 
-int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
+int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) try {
   if (!b) return CPBUS_EINVAL;
   if (!b->K || b->h_timers.empty()) return CPBUS_ENOENT;
   const uint32_t slot_index = timer_id & kTimerSlotMask, gen = timer_id >> kTimerSlotBits;
@@ -1010,9 +1016,9 @@ int cpbus_timer_cancel(cpbus_t* b, uint32_t timer_id) {
   CK(cudaStreamSynchronize(b->stream));
   if (b->n_timers == 0) b->min_period = UINT64_MAX;
   return push_mask_words(b, l, 1);
-}
+} CPBUS_CATCH
 
-int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) {
+int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) try {
   if (!b || (!ev && n)) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   for (size_t i = 0; i < n; i++) {   // counter slots of the whole burst: requested up front, touched in the loop below
@@ -1039,9 +1045,9 @@ int cpbus_publish(cpbus_t* b, const cpbus_event* ev, size_t n) {
   }
   dbg_tail(n);                                                   // events/bus.go:139
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_send(cpbus_t* b, uint32_t sub_id, const cpbus_event* ev) {
+int cpbus_send(cpbus_t* b, uint32_t sub_id, const cpbus_event* ev) try {
   if (!b || !ev || ev->code >= CPBUS_N_CODES) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
@@ -1050,9 +1056,9 @@ int cpbus_send(cpbus_t* b, uint32_t sub_id, const cpbus_event* ev) {
   if ((rc = stage_one(b, ev->code, ev->source_id, sub_id, CPBUS_F_UNICAST))) return rc;
   b->st.publishes++;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_advance(cpbus_t* b, uint64_t now_ns) {
+int cpbus_advance(cpbus_t* b, uint64_t now_ns) try {
   if (!b) return CPBUS_EINVAL;
   if (now_ns < b->now) return CPBUS_EORDER;
   if (now_ns == b->now) return CPBUS_OK;
@@ -1066,20 +1072,20 @@ int cpbus_advance(cpbus_t* b, uint64_t now_ns) {
   }
   b->now = now_ns;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_flush(cpbus_t* b) {
+int cpbus_flush(cpbus_t* b) try {
   if (!b) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   return flush_staged(b, b->now);
-}
+} CPBUS_CATCH
 
-int cpbus_sync(cpbus_t* b) {
+int cpbus_sync(cpbus_t* b) try {
   if (!b) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaStreamSynchronize(b->stream));
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged,
                                const void* d_next, size_t n_next);
@@ -1094,7 +1100,8 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
 // that fell behind fires late, never "not at all".)
 static int publish_device_split(cpbus_t* b, const cpbus_event* d_events, size_t n, uint64_t watermark_ns, bool staged,
                                 const void* d_next, size_t n_next) {
-  std::vector<uint64_t> ts(n);
+  std::vector<uint64_t> ts;
+  try { ts.resize(n); } catch (const std::bad_alloc&) { return CPBUS_ENOMEM; }   // (no exception may cross the C boundary)
   if (n) {
     CK(cudaMemcpy2DAsync(ts.data(), 8, reinterpret_cast<const unsigned char*>(d_events) + offsetof(cpbus_event, ts_ns), sizeof(cpbus_event),
                          8, n, cudaMemcpyDeviceToHost, b->stream));
@@ -1165,20 +1172,20 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
   return CPBUS_OK;
 }
 
-int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) {
+int cpbus_publish_device(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns) try {
   return publish_device_impl(b, d_events, n, watermark_ns, false, nullptr, 0);
-}
+} CPBUS_CATCH
 
 // Multi-GPU ingest fused into the fan-out kernel: d_events (and d_next) may point into ANOTHER GPU's HBM (the
 // publisher's event stream, peer-mapped over NVLink).  One CTA pulls the batch across the link, stages it in local
 // HBM and publishes it with the batch descriptor; if the caller names the NEXT batch, that one is pulled by the
 // same launch while its stores are in flight, so the following call starts from local memory.  No collective.
-int cpbus_publish_device_staged(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, const void* d_next, size_t n_next) {
+int cpbus_publish_device_staged(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, const void* d_next, size_t n_next) try {
   return publish_device_impl(b, d_events, n, watermark_ns, true, d_next, n_next);
-}
+} CPBUS_CATCH
 
 // ---- buffers shared between the GPUs of one box (CUDA IPC; NVLink peer mapping on the importing side) ----
-int cpbus_shared_alloc(cpbus_t* b, size_t bytes, void** dptr, unsigned char handle[64]) {
+int cpbus_shared_alloc(cpbus_t* b, size_t bytes, void** dptr, unsigned char handle[64]) try {
   if (!b || !dptr || !handle || !bytes) return CPBUS_EINVAL;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   int rc = dev_guard(b); if (rc) return rc;
@@ -1191,9 +1198,9 @@ int cpbus_shared_alloc(cpbus_t* b, size_t bytes, void** dptr, unsigned char hand
   b->shared_owned.push_back(p);
   *dptr = p;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_shared_open(cpbus_t* b, const unsigned char handle[64], void** dptr) {
+int cpbus_shared_open(cpbus_t* b, const unsigned char handle[64], void** dptr) try {
   if (!b || !dptr || !handle) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;      // the IMPORTING device must be current: the mapping is made for it
   cudaIpcMemHandle_t h;
@@ -1203,9 +1210,9 @@ int cpbus_shared_open(cpbus_t* b, const unsigned char handle[64], void** dptr) {
   b->shared_mapped.push_back(p);
   *dptr = p;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_shared_close(cpbus_t* b, void* dptr) {
+int cpbus_shared_close(cpbus_t* b, void* dptr) try {
   if (!b || !dptr) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaStreamSynchronize(b->stream));
@@ -1215,7 +1222,7 @@ int cpbus_shared_close(cpbus_t* b, void* dptr) {
   for (size_t i = 0; i < b->shared_mapped.size(); i++)
     if (b->shared_mapped[i] == dptr) { cudaIpcCloseMemHandle(dptr); b->shared_mapped.erase(b->shared_mapped.begin() + i); return CPBUS_OK; }
   return CPBUS_ENOENT;
-}
+} CPBUS_CATCH
 
 // ---- the publisher's event stream across the GPUs of one box (include/cpbus.h: cpbus_stream_*) ----
 struct cpbus_stream {
@@ -1245,7 +1252,7 @@ static int stream_bind(cpbus_stream* st) {
   return CPBUS_OK;
 }
 
-int cpbus_stream_create(cpbus_t* b, uint32_t n_slots, uint32_t n_consumers, cpbus_stream_t** out, unsigned char handle[64]) {
+int cpbus_stream_create(cpbus_t* b, uint32_t n_slots, uint32_t n_consumers, cpbus_stream_t** out, unsigned char handle[64]) try {
   if (!b || !out || !handle || n_slots < 4 || n_consumers == 0 || n_consumers > kStreamMaxConsumers) return CPBUS_EINVAL;
   if (b->lossless) return CPBUS_EINVAL;   // admission would have to see every shard: throughput mode only
   *out = nullptr;
@@ -1274,9 +1281,9 @@ int cpbus_stream_create(cpbus_t* b, uint32_t n_slots, uint32_t n_consumers, cpbu
   if (cudaMallocHost((void**)&st->h_ack, (size_t)kStreamMaxConsumers * 32) != cudaSuccess) return fail(CPBUS_ENOMEM);
   *out = st;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_stream_open(cpbus_t* b, const unsigned char handle[64], uint32_t consumer_index, cpbus_stream_t** out) {
+int cpbus_stream_open(cpbus_t* b, const unsigned char handle[64], uint32_t consumer_index, cpbus_stream_t** out) try {
   if (!b || !out || !handle || consumer_index == 0 || consumer_index >= kStreamMaxConsumers) return CPBUS_EINVAL;
   if (b->lossless) return CPBUS_EINVAL;
   *out = nullptr;
@@ -1300,11 +1307,11 @@ int cpbus_stream_open(cpbus_t* b, const unsigned char handle[64], uint32_t consu
   b->streams.push_back(st);
   *out = st;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Same-process consumer (one host process driving several GPUs, as a cgo shim would): no IPC handle — the owner's
 // pointer is used directly, with peer access enabled when the consumer's bus lives on another GPU.
-int cpbus_stream_attach(cpbus_t* b, cpbus_stream_t* owner, uint32_t consumer_index, cpbus_stream_t** out) {
+int cpbus_stream_attach(cpbus_t* b, cpbus_stream_t* owner, uint32_t consumer_index, cpbus_stream_t** out) try {
   if (!b || !owner || !owner->owner || !out || consumer_index == 0 || consumer_index >= owner->n_consumers) return CPBUS_EINVAL;
   if (b->lossless || b->B != owner->B) return CPBUS_EINVAL;
   *out = nullptr;
@@ -1325,9 +1332,9 @@ int cpbus_stream_attach(cpbus_t* b, cpbus_stream_t* owner, uint32_t consumer_ind
   b->streams.push_back(st);
   *out = st;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_stream_close(cpbus_stream_t* st) {
+int cpbus_stream_close(cpbus_stream_t* st) try {
   if (!st) return CPBUS_EINVAL;
   cpbus* b = st->bus;
   cudaSetDevice(b->device);
@@ -1343,21 +1350,21 @@ int cpbus_stream_close(cpbus_stream_t* st) {
   b->streams.erase(std::remove(b->streams.begin(), b->streams.end(), st), b->streams.end());
   delete st;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_stream_set_timeout(cpbus_stream_t* st, uint32_t microseconds) {
+int cpbus_stream_set_timeout(cpbus_stream_t* st, uint32_t microseconds) try {
   if (!st) return CPBUS_EINVAL;
   st->bus->stream_spin_us = microseconds;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_stream_status(cpbus_stream_t* st) {
+int cpbus_stream_status(cpbus_stream_t* st) try {
   if (!st) return CPBUS_EINVAL;
   return (*(volatile unsigned int*)st->bus->h_err) ? CPBUS_ETIMEDOUT : CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Publisher: copy the batch into the next slot, then release it (header after payload, same stream).
-int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64_t now_ns, uint32_t flags) {
+int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64_t now_ns, uint32_t flags) try {
   if (!st || !st->owner || (!ev && n) || n > st->B) return CPBUS_EINVAL;
   cpbus* b = st->bus;
   int rc = dev_guard(b); if (rc) return rc;
@@ -1401,11 +1408,11 @@ int cpbus_stream_put(cpbus_stream_t* st, const cpbus_event* ev, size_t n, uint64
   CK(cudaEventRecord(st->staged_done[s], st->put_stream));
   st->put_seq = q;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Consumers that are NOT told n / now_ns by their driver: look at the next slot's header (one 32-byte copy across the link).
 // *ready = 0: the publisher has not released that batch yet.
-int cpbus_stream_poll(cpbus_stream_t* st, int* ready, size_t* n, uint64_t* now_ns) {
+int cpbus_stream_poll(cpbus_stream_t* st, int* ready, size_t* n, uint64_t* now_ns) try {
   if (!st || !ready) return CPBUS_EINVAL;
   cpbus* b = st->bus;
   int rc = dev_guard(b); if (rc) return rc;
@@ -1417,10 +1424,10 @@ int cpbus_stream_poll(cpbus_stream_t* st, int* ready, size_t* n, uint64_t* now_n
   *ready = h.seq == q ? 1 : 0;
   if (*ready) { if (n) *n = h.n; if (now_ns) *now_ns = h.watermark; }
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Every rank (the publisher's included): fan out the next batch of the stream to this GPU's shard.
-int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns) {
+int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns) try {
   if (!st || n > st->B) return CPBUS_EINVAL;
   cpbus* b = st->bus;
   int rc = dev_guard(b); if (rc) return rc;
@@ -1440,7 +1447,7 @@ int cpbus_stream_fanout(cpbus_stream_t* st, size_t n, uint64_t now_ns) {
   st->get_seq = q;
   b->st.publishes += n; b->seq += n;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 static int read_cursors(cpbus* b, uint32_t l, uint64_t* tail, uint64_t* head, uint64_t* lost = nullptr) {
   SubCtl c{};
@@ -1463,7 +1470,7 @@ static int copy_slots(cpbus* b, uint32_t l, uint64_t from, size_t n, cpbus_event
   return CPBUS_OK;
 }
 
-int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n, uint64_t* lost) {
+int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n, uint64_t* lost) try {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
@@ -1480,12 +1487,12 @@ int cpbus_drain(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_
   CK(cudaStreamSynchronize(b->stream));
   *n = take;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Bulk drain: everything undrained in mailboxes [first_sub, first_sub+n) in ONE kernel + two D2H copies.
 // out receives the records (each mailbox's run contiguous and FIFO), offsets[i]/counts[i] say where mailbox i's run is.
 int cpbus_drain_many(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_event* out, size_t cap, uint32_t* offsets,
-                     uint32_t* counts, size_t* total) {
+                     uint32_t* counts, size_t* total) try {
   if (!b || !n || !out || !cap || !offsets || !counts || !total || cap > 0xFFFFFFFFull) return CPBUS_EINVAL;
   const uint32_t l = first_sub - b->cfg.sub_id_base;
   if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
@@ -1514,10 +1521,10 @@ int cpbus_drain_many(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_event* ou
   CK(cudaStreamSynchronize(b->stream));
   *total = tot;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // Device-side consumer: every mailbox of this shard is read to the end and its records are discarded.
-int cpbus_consume_all(cpbus_t* b) {
+int cpbus_consume_all(cpbus_t* b) try {
   if (!b) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
@@ -1529,9 +1536,9 @@ int cpbus_consume_all(cpbus_t* b) {
   }
   b->room_lb = b->R;   // stream-ordered behind every earlier fan-out: from here on every mailbox is empty
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_peek_window(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n) {
+int cpbus_peek_window(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap, size_t* n) try {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
   const uint32_t l = sub_id - b->cfg.sub_id_base;
   if (sub_id < b->cfg.sub_id_base || l >= b->n_next) return CPBUS_ENOENT;
@@ -1543,9 +1550,9 @@ int cpbus_peek_window(cpbus_t* b, uint32_t sub_id, cpbus_event* out, size_t cap,
   if (take && (rc = copy_slots(b, l, tail - take, take, out))) return rc;
   *n = take;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out) {
+int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out) try {
   if (!b || !out || !n) return CPBUS_EINVAL;
   const uint32_t l = first_sub - b->cfg.sub_id_base;
   if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
@@ -1556,9 +1563,9 @@ int cpbus_digest(cpbus_t* b, uint32_t first_sub, uint32_t n, cpbus_digest_t* out
   CK(cudaStreamSynchronize(b->stream));
   for (uint32_t i = 0; i < n; i++) { out[i].count = c[i].tail; out[i].digest = c[i].digest; }
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_digest_fold_begin(cpbus_t* b, uint32_t first_sub, uint32_t n, uint32_t* ticket) {
+int cpbus_digest_fold_begin(cpbus_t* b, uint32_t first_sub, uint32_t n, uint32_t* ticket) try {
   if (!b || !ticket || !n) return CPBUS_EINVAL;
   const uint32_t l = first_sub - b->cfg.sub_id_base;
   if (first_sub < b->cfg.sub_id_base || (uint64_t)l + n > b->n_next) return CPBUS_ENOENT;
@@ -1575,25 +1582,25 @@ int cpbus_digest_fold_begin(cpbus_t* b, uint32_t first_sub, uint32_t n, uint32_t
   CK(cudaEventRecord(b->fold_done[slot], b->stream));
   *ticket = slot;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_digest_fold_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
+int cpbus_digest_fold_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) try {
   if (!b || !out || ticket >= (uint32_t)cpbus::kFoldSlots) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaEventSynchronize(b->fold_done[ticket]));
   for (int i = 0; i < 4; i++) out[i] = b->h_fold[4 * ticket + i];
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4]) {
+int cpbus_digest_fold(cpbus_t* b, uint32_t first_sub, uint32_t n, uint64_t out[4]) try {
   uint32_t ticket = 0;
   int rc = cpbus_digest_fold_begin(b, first_sub, n, &ticket);
   return rc ? rc : cpbus_digest_fold_end(b, ticket, out);
-}
+} CPBUS_CATCH
 
 // The fan-out kernel leaves {deliveries, ticks, sum of the new digests} of each launch in a small ring;
 // reading a step's result therefore costs one 256-byte D2H and no extra kernel.
-int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) {
+int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) try {
   if (!b || !ticket) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
@@ -1607,9 +1614,9 @@ int cpbus_step_result_begin(cpbus_t* b, uint32_t* ticket) {
   CK(cudaEventRecord(b->result_done[t], b->result_stream));
   *ticket = t;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_step_result_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
+int cpbus_step_result_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) try {
   if (!b || !out || ticket >= 8) return CPBUS_EINVAL;
   int rc = dev_guard(b); if (rc) return rc;
   CK(cudaEventSynchronize(b->result_done[ticket]));
@@ -1619,7 +1626,7 @@ int cpbus_step_result_end(cpbus_t* b, uint32_t ticket, uint64_t out[4]) {
     out[0] += r.deliveries; out[1] += r.ticks; out[2] += r.digest_sum; out[3] += r.launch_seq;
   }
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // DebugEvents — events/bus.go:34-54
 // Broadcast events of device-published batches join the debug ring here, in publish order (the kernel's lead CTA kept
@@ -1643,7 +1650,7 @@ static int dbg_resolve(cpbus* b) {
   return CPBUS_OK;
 }
 
-int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) {
+int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) try {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
   { const int rc = dbg_resolve(b); if (rc) return rc; }
   size_t k = 0;
@@ -1658,9 +1665,9 @@ int cpbus_debug_events(cpbus_t* b, cpbus_event* out, size_t cap, size_t* n) {
   }
   *n = k;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
+int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) try {
   if (!b || !out) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
@@ -1683,11 +1690,11 @@ int cpbus_stats(cpbus_t* b, cpbus_stats_t* out) {
   *out = b->st;
   for (int c = 0; c < CPBUS_N_CODES; c++) out->published_by_code[c] += b->h_acct->by_code[c];   // device-published batches (kernel-counted)
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 // containerpilot_events{code, source} (events/bus.go:60-68,130-132): host publishes are counted in cpbus_publish, batches
 // that arrive in device memory by the fan-out kernel's lead CTA (DevPubAcct).
-int cpbus_publish_counts(cpbus_t* b, cpbus_pair_count* out, size_t cap, size_t* n) {
+int cpbus_publish_counts(cpbus_t* b, cpbus_pair_count* out, size_t cap, size_t* n) try {
   if (!b || !n || (!out && cap)) return CPBUS_EINVAL;
   std::lock_guard<std::mutex> g(b->mu);
   int rc = dev_guard(b); if (rc) return rc;
@@ -1705,13 +1712,13 @@ int cpbus_publish_counts(cpbus_t* b, cpbus_pair_count* out, size_t cap, size_t* 
   for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = cpbus_pair_count{(uint32_t)(v[i].first >> 32), (uint32_t)v[i].first, v[i].second};
   *n = v.size();
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
-int cpbus_device_ptrs(cpbus_t* b, void** ring, void** ctl) {
+int cpbus_device_ptrs(cpbus_t* b, void** ring, void** ctl) try {
   if (!b) return CPBUS_EINVAL;
   if (ring) *ring = b->d_ring;
   if (ctl) *ctl = b->d_ctl;
   return CPBUS_OK;
-}
+} CPBUS_CATCH
 
 }  // extern "C"

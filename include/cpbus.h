@@ -350,7 +350,8 @@ uint64_t cpbus_digest_multiplier(void);
  * out[] receives the indices i < n with active[i] != 0 (active == NULL: all), grouped per block of `block` consecutive
  * subscribers (0 = the library's policy from n and ring_cap: one block up to 16 GiB of rings, 8-GiB blocks beyond;
  * 0xFFFFFFFF = one block), inside a block by code mask — equal masks adjacent — and, with heavy_first, masks with more
- * codes first.  Returns the number of indices written.  Delivery results never depend on this order. */
+ * codes first.  out must have room for n indices; returns how many were written (0 on bad arguments).  Delivery
+ * results never depend on this order. */
 size_t cpbus_mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block,
                         int heavy_first, uint32_t* out);
 
