@@ -80,6 +80,33 @@ def test_dense_throughput_mode_window(store, batch_cap):
 
 
 @pytest.mark.parametrize("store", STORES)
+@pytest.mark.parametrize("K,zipf", [(0, None), (1, None), (0, 1.0), (2, 1.0)])
+def test_largest_batches(store, K, zipf):
+    """batch_cap = 1024, the largest a launch takes (every thread moves 8 chunks in the planar re-layout; 32 chunks of 32 events
+    in the filter passes): dense, dense + ticks, filtered (ORDERED) and filtered + ticks + unicast, ragged last batch."""
+    n_subs, n_events, B, R = 200, 1024 * 3 + 517, 1024, 4096
+    rng = np.random.default_rng(77 + K)
+    masks = tr.zipf_masks(n_subs, zipf, 3) if zipf else np.full(n_subs, nat.MASK_ALL, dtype=np.uint32)
+    codes = (tr.zipf_codes(n_events, zipf, 4) if zipf else rng.integers(0, 17, n_events)).astype(np.uint32)
+    srcs = rng.integers(0, 4096, n_events).astype(np.uint32)
+    orc = ob.Oracle(n_subs, timers_per_sub=K, keep_window=R)
+    with Bus(n_subs, ring_cap=R, batch_cap=B, timers_per_sub=K, store_path=store) as bus:
+        for s, m in enumerate(masks):
+            orc.subscribe(int(m)); bus.subscribe(int(m))
+            for j in range(K):
+                orc.timer_add(s, 40_000 + 977 * s + 13 * j, 5000 + 2 * s + j, False); bus.timer_add(s, 40_000 + 977 * s + 13 * j, 5000 + 2 * s + j, False)
+        for i in range(n_events):
+            if i % 64 == 0:
+                assert orc.advance(i * 500) == 0; nat.check(bus.advance(i * 500), "advance")
+            if K == 2 and i % 97 == 0:
+                orc.receive(i % n_subs, 7, 9); nat.check(bus.send(i % n_subs, 7, 9), "send")
+            orc.publish(int(codes[i]), int(srcs[i])); nat.check(bus.publish(int(codes[i]), int(srcs[i])), "publish")
+        nat.check(bus.flush(), "flush"); bus.sync()
+        st = tr.compare(bus, orc, n_subs, window=R)
+        assert st["batches"] <= n_events // B + 2 + (n_events // 64 if K else 0)
+
+
+@pytest.mark.parametrize("store", STORES)
 @pytest.mark.parametrize("seed,K", [(1, 0), (2, 1), (3, 2), (4, 4), (5, 8)])
 def test_random_mixed_traces(store, seed, K):
     """Filters, unicast sends, membership changes, clock advances, periodic and one-shot timers."""
