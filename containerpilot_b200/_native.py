@@ -114,6 +114,7 @@ SYMBOLS = {
     "cpbus_strerror": (C.c_char_p, [C.c_int]),
     "cpbus_last_cuda_error": (C.c_char_p, []),
     "cpbus_abi_version": (C.c_uint32, []),
+    "cpbus_split_plan": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "cpbus_mask_order": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "cpbus_record_hash": (C.c_uint64, [_P(Event)]),
     "cpbus_digest_multiplier": (C.c_uint64, []),

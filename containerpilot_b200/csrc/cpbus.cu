@@ -538,6 +538,18 @@ extern "C" {
   catch (...) { snprintf(g_cuda_err, sizeof(g_cuda_err), "unexpected C++ exception"); return CPBUS_ECUDA; }
 
 uint32_t cpbus_abi_version(void) { return 2; }
+static int split_plan(const uint64_t* ts, size_t n, uint32_t batch_cap, uint64_t now, uint64_t watermark, uint64_t window,
+                      std::vector<size_t>& end, std::vector<uint64_t>& wm);
+int cpbus_split_plan(const uint64_t* ts, size_t n, uint32_t batch_cap, uint64_t now_ns, uint64_t watermark_ns, uint64_t window_ns,
+                     size_t* ends, uint64_t* watermarks, size_t cap, size_t* n_slices) try {
+  if ((!ts && n) || !n_slices || (cap && (!ends || !watermarks))) return CPBUS_EINVAL;
+  std::vector<size_t> end; std::vector<uint64_t> wm;
+  const int rc = split_plan(ts, n, batch_cap, now_ns, watermark_ns, window_ns, end, wm);
+  if (rc) return rc;
+  *n_slices = end.size();
+  for (size_t k = 0; k < end.size() && k < cap; k++) { ends[k] = end[k]; watermarks[k] = wm[k]; }
+  return CPBUS_OK;
+} CPBUS_CATCH
 size_t cpbus_mask_order(const uint32_t* masks, const uint8_t* active, uint32_t n, uint32_t ring_cap, uint32_t block, int heavy_first, uint32_t* out) {
   if (!masks || !out || !ring_cap) return 0;
   try {
@@ -1098,31 +1110,48 @@ static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint6
 // a tick is ordered in front of every event with ts >= its due time and such events are either in this slice behind it or
 // in a later one.  The host path does the same at cpbus_advance.  (events/timer.go:40-71 has no such limit: a Go timer
 // that fell behind fires late, never "not at all".)
+// The cut itself, host-only (exported as cpbus_split_plan so that it can be tested without a GPU): slice k = records
+// [end[k-1], end[k]) launched with watermark wm[k].  `now` = the bus clock (= the last launched watermark once staged events
+// are flushed), `window` = the widest watermark step one launch may take (UINT64_MAX: no timer armed).
+static int split_plan(const uint64_t* ts, size_t n, uint32_t batch_cap, uint64_t now, uint64_t watermark, uint64_t window,
+                      std::vector<size_t>& end, std::vector<uint64_t>& wm) {
+  for (size_t i = 1; i < n; i++) if (ts[i] < ts[i - 1]) return CPBUS_EORDER;
+  if (!batch_cap || !window) return CPBUS_EINVAL;
+  if (watermark < now || (n && ts[n - 1] > watermark)) return CPBUS_EORDER;
+  size_t i = 0;
+  uint64_t lw = now;
+  for (;;) {
+    const uint64_t edge = (window == UINT64_MAX || watermark - lw <= window) ? watermark : lw + window;
+    size_t j = std::upper_bound(ts + i, ts + n, edge) - ts;
+    uint64_t w = edge;
+    if (j - i > batch_cap) { j = i + batch_cap; w = std::max(ts[j - 1], lw); }   // (records older than the clock ride with it)
+    end.push_back(j); wm.push_back(w);
+    i = j; lw = w;
+    if (j == n && w == watermark) return CPBUS_OK;
+  }
+}
+
 static int publish_device_split(cpbus_t* b, const cpbus_event* d_events, size_t n, uint64_t watermark_ns, bool staged,
                                 const void* d_next, size_t n_next) {
-  std::vector<uint64_t> ts;
-  try { ts.resize(n); } catch (const std::bad_alloc&) { return CPBUS_ENOMEM; }   // (no exception may cross the C boundary)
+  std::vector<uint64_t> ts, wm;
+  std::vector<size_t> end;
+  ts.resize(n);
   if (n) {
     CK(cudaMemcpy2DAsync(ts.data(), 8, reinterpret_cast<const unsigned char*>(d_events) + offsetof(cpbus_event, ts_ns), sizeof(cpbus_event),
                          8, n, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    for (size_t i = 1; i < n; i++) if (ts[i] < ts[i - 1]) return CPBUS_EORDER;
-    if (ts[n - 1] > watermark_ns) return CPBUS_EORDER;
   }
+  int rc = split_plan(ts.data(), n, b->B, b->now, watermark_ns, max_window(b), end, wm);   // (a one-shot retiring mid-way can only widen the window)
+  if (rc) return rc;
   size_t i = 0;
-  for (;;) {
-    const uint64_t win = max_window(b);   // (re-read: a one-shot retiring mid-way can only widen it)
-    const uint64_t edge = (win == UINT64_MAX || watermark_ns - b->last_watermark <= win) ? watermark_ns : b->last_watermark + win;
-    size_t j = std::upper_bound(ts.begin() + i, ts.end(), edge) - ts.begin();
-    uint64_t w = edge;
-    if (j - i > b->B) { j = i + b->B; w = ts[j - 1]; }
-    const bool last = j == n && w == watermark_ns;
-    const int rc = publish_device_impl(b, d_events + i, j - i, w, staged, last ? d_next : nullptr, last ? n_next : 0);
+  for (size_t k = 0; k < end.size(); k++) {
+    const bool last = k + 1 == end.size();
+    rc = publish_device_impl(b, d_events + i, end[k] - i, wm[k], staged, last ? d_next : nullptr, last ? n_next : 0);
     if (rc) return rc;
     b->st.device_splits++;
-    i = j;
-    if (last) return CPBUS_OK;
+    i = end[k];
   }
+  return CPBUS_OK;
 }
 
 static int publish_device_impl(cpbus_t* b, const void* d_events, size_t n, uint64_t watermark_ns, bool staged,

@@ -346,6 +346,12 @@ uint32_t cpbus_abi_version(void);
  * oracle and external checkers can reproduce it without reading kernel code) */
 uint64_t cpbus_record_hash(const cpbus_event* ev);
 uint64_t cpbus_digest_multiplier(void);
+/* How cpbus_publish_device cuts a batch one launch cannot take, as a pure host function (no device needed): ts[0..n) = the
+ * records' timestamps (sorted), now_ns = the bus clock, window_ns = the widest watermark step of one launch (UINT64_MAX: no
+ * timer armed).  Slice k = records [ends[k-1], ends[k]) with watermark watermarks[k]; *n_slices = how many there are (the
+ * first `cap` are written).  CPBUS_EORDER: unsorted, a record beyond watermark_ns, or watermark_ns < now_ns. */
+int cpbus_split_plan(const uint64_t* ts, size_t n, uint32_t batch_cap, uint64_t now_ns, uint64_t watermark_ns, uint64_t window_ns,
+                     size_t* ends, uint64_t* watermarks, size_t cap, size_t* n_slices);
 /* The order in which the filtered (ORDERED) fan-out walks the mailboxes, as a pure host function (no device needed):
  * out[] receives the indices i < n with active[i] != 0 (active == NULL: all), grouped per block of `block` consecutive
  * subscribers (0 = the library's policy from n and ring_cap: one block up to 16 GiB of rings, 8-GiB blocks beyond;

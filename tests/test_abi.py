@@ -168,3 +168,57 @@ def test_mask_order_host_logic():
     assert first.max() < (1 << 18) and (first[: 1 << 17] % 2 == 0).all() and (first[1 << 17:] % 2 == 1).all()
     o2 = _mask_order(big[: 1 << 19], None, 1024, 0, True)                            # 16 GiB: one global block
     assert (o2[: 1 << 18] % 2 == 0).all()
+
+
+def _split_plan(ts, B, now, wm, window):
+    lib = nat.load()
+    ts = np.ascontiguousarray(ts, dtype=np.uint64)
+    n_sl = C.c_size_t()
+    rc = lib.cpbus_split_plan(ts.ctypes.data if len(ts) else None, len(ts), B, now, wm, window, None, None, 0, C.byref(n_sl))
+    if rc:
+        return rc, None, None
+    ends = np.zeros(n_sl.value, dtype=np.uintp); wms = np.zeros(n_sl.value, dtype=np.uint64)
+    assert lib.cpbus_split_plan(ts.ctypes.data if len(ts) else None, len(ts), B, now, wm, window, ends.ctypes.data, wms.ctypes.data, n_sl.value, C.byref(n_sl)) == 0
+    return 0, ends.astype(np.int64), wms
+
+
+def test_split_plan_host_logic():
+    """How an oversize / wide-window device batch is cut (host-only): slices are contiguous, at most batch_cap long, their
+    watermarks never decrease, step at most one window, cover their records, end exactly at the caller's watermark, and no
+    record older than a slice's watermark is left for a later slice."""
+    UMAX = (1 << 64) - 1
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        B = int(rng.choice([32, 64, 256, 1024]))
+        n = int(rng.choice([0, 1, B - 1, B, B + 1, 3 * B + 7, int(rng.integers(0, 5 * B))]))
+        now = int(rng.integers(0, 10_000))
+        span = int(rng.choice([0, 1, 50, 100_000]))
+        window = [UMAX, 1, 7, 1000, 33_000][int(rng.integers(0, 5))]                            # (a Python int: numpy would make 2^64-1 a float)
+        ts = np.sort(rng.integers(max(0, now - 20), now + span + 1, n)).astype(np.uint64)     # a few records older than the clock are legal
+        wm = now + span + int(rng.choice([0, 0, 5, 40_000]))
+        if window == 1 and wm - now > 5000:
+            window = 7                                                                         # (keep the number of slices sane)
+        rc, ends, wms = _split_plan(ts, B, now, wm, window)
+        assert rc == 0
+        begins = np.concatenate(([0], ends[:-1]))
+        assert (ends >= begins).all() and ends[-1] == n and (ends - begins <= B).all()
+        assert (np.diff(wms.astype(object)) >= 0).all() and int(wms[-1]) == wm and int(wms[0]) >= now
+        steps = np.diff(np.concatenate(([now], wms)).astype(object))
+        if window != UMAX:
+            assert max(steps) <= window
+        prev = now
+        for b0, e0, w in zip(begins, ends, wms):
+            if e0 > b0:
+                assert int(ts[e0 - 1]) <= int(w)                                               # the slice's records are not beyond its watermark
+            if e0 < n and int(ts[e0]) < int(w):
+                # a record older than a slice's watermark may only be left behind by a SIZE cut among records that were
+                # already older than the clock (they ride with it: the watermark did not move)
+                assert e0 - b0 == B and int(w) == prev
+            prev = int(w)
+        if n <= B and (window == UMAX or wm - now <= window):
+            assert len(ends) == 1                                                              # nothing to cut
+    # refusals
+    assert _split_plan(np.array([5, 4], dtype=np.uint64), 32, 0, 10, UMAX)[0] == nat.EORDER    # unsorted
+    assert _split_plan(np.array([5, 11], dtype=np.uint64), 32, 0, 10, UMAX)[0] == nat.EORDER   # beyond the watermark
+    assert _split_plan(np.array([], dtype=np.uint64), 32, 10, 9, UMAX)[0] == nat.EORDER        # clock would move backwards
+    assert _split_plan(np.array([1], dtype=np.uint64), 32, 0, 10, 0)[0] == nat.EINVAL
